@@ -1,0 +1,493 @@
+// Device L-BFGS-B (unbounded case) - one CTA minimises the negative ELBO of one gene-model.
+//
+// Replaces `gpflow.optimizers.Scipy().minimize(..., options=dict(maxiter=5000))`
+// (GPcounts/GPcounts_Module.py:692-697) = SciPy L-BFGS-B v3.0 with SciPy defaults
+// (m = 10, ftol = 2.22e-9, gtol = 1e-5, maxls = 20, maxfun = 15000).  The reference's results depend on
+// where this optimiser stops, so the iteration is restated step for step
+// (CPU twin: oracle/lbfgsb.py, itself checked against the installed SciPy):
+//   * empty memory: generalised Cauchy point z = x - g/theta, first step min(1/|d|, 1e10), later steps 1
+//   * otherwise the quasi-Newton direction through the compact representation (formk / subsm with all
+//     variables free), d = z - x
+//   * More'-Thuente dcsrch / dcstep with ftol 1e-3, gtol 0.9, xtol 0.1, at most maxls trial points
+//   * convergence: max|g| <= gtol, or (fold - f) <= ftol * max(|fold|, |f|, 1) after an accepted step
+//   * pair accepted iff dr > epsmch * ddum; theta = rr / dr; memory refreshed when a factorisation or
+//     the line search fails; abnormal termination when that happens with an empty memory
+// All scalar logic is executed redundantly by every thread on CTA-uniform values.
+#pragma once
+#include "model.cuh"
+
+#define GPC_MMAX 10
+#define GPC_EPSMCH 2.220446049250313e-16
+
+enum { TASK_PGTOL = 0, TASK_FTOL = 1, TASK_LIMIT = 2, TASK_ABNORMAL = 3, TASK_CHOL = 4 };
+
+struct OptSmem {
+    double SS[GPC_MMAX][GPC_MMAX];     // s_i . s_j (symmetric, logical order = oldest first)
+    double SY[GPC_MMAX][GPC_MMAX];     // lower incl. diagonal: s_i . y_j (i >= j), diagonal = dr   (matupd)
+    double YY[GPC_MMAX][GPC_MMAX];     // y_i . y_j
+    double RZ[GPC_MMAX][GPC_MMAX];     // upper incl. diagonal: s_i . y_j (i <= j) by explicit dots  (formk)
+    double WN[2 * GPC_MMAX][2 * GPC_MMAX];   // upper-triangular LEL^T factor of the middle matrix
+    double wv[2 * GPC_MMAX];
+    double dots[GPC_MMAX][6];          // per memory vector: S.d, Y.d, S.r, Y.r, S.g, Y.g
+    int info;
+};
+
+struct DcsrchState {
+    bool brackt;
+    int stage;
+    double finit, ginit, gtest, width, width1, stx, fx, gx, sty, fy, gy, stmin, stmax, stp;
+};
+
+__device__ __forceinline__ void dcstep(double& stx, double& fx, double& dx, double& sty, double& fy, double& dy,
+                                       double& stp, double fp, double dp, bool& brackt, double stpmin, double stpmax) {
+    const double sgnd = dp * (dx / fabs(dx));
+    double stpf, stpc, stpq, theta, s, gamma, p, q, r;
+    if (fp > fx) {
+        theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+        s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
+        gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
+        if (stp < stx) gamma = -gamma;
+        p = (gamma - dx) + theta;
+        q = ((gamma - dx) + gamma) + dp;
+        r = p / q;
+        stpc = stx + r * (stp - stx);
+        stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / 2.0) * (stp - stx);
+        if (fabs(stpc - stx) < fabs(stpq - stx)) stpf = stpc; else stpf = stpc + (stpq - stpc) / 2.0;
+        brackt = true;
+    } else if (sgnd < 0.0) {
+        theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+        s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
+        gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
+        if (stp > stx) gamma = -gamma;
+        p = (gamma - dp) + theta;
+        q = ((gamma - dp) + gamma) + dx;
+        r = p / q;
+        stpc = stp + r * (stx - stp);
+        stpq = stp + (dp / (dp - dx)) * (stx - stp);
+        if (fabs(stpc - stp) > fabs(stpq - stp)) stpf = stpc; else stpf = stpq;
+        brackt = true;
+    } else if (fabs(dp) < fabs(dx)) {
+        theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+        s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
+        gamma = s * sqrt(fmax(0.0, (theta / s) * (theta / s) - (dx / s) * (dp / s)));
+        if (stp > stx) gamma = -gamma;
+        p = (gamma - dp) + theta;
+        q = (gamma + (dx - dp)) + gamma;
+        r = p / q;
+        if (r < 0.0 && gamma != 0.0) stpc = stp + r * (stx - stp);
+        else if (stp > stx) stpc = stpmax;
+        else stpc = stpmin;
+        stpq = stp + (dp / (dp - dx)) * (stx - stp);
+        if (brackt) {
+            if (fabs(stpc - stp) < fabs(stpq - stp)) stpf = stpc; else stpf = stpq;
+            if (stp > stx) stpf = fmin(stp + 0.66 * (sty - stp), stpf);
+            else stpf = fmax(stp + 0.66 * (sty - stp), stpf);
+        } else {
+            if (fabs(stpc - stp) > fabs(stpq - stp)) stpf = stpc; else stpf = stpq;
+            stpf = fmin(stpmax, stpf);
+            stpf = fmax(stpmin, stpf);
+        }
+    } else {
+        if (brackt) {
+            theta = 3.0 * (fp - fy) / (sty - stp) + dy + dp;
+            s = fmax(fabs(theta), fmax(fabs(dy), fabs(dp)));
+            gamma = s * sqrt((theta / s) * (theta / s) - (dy / s) * (dp / s));
+            if (stp > sty) gamma = -gamma;
+            p = (gamma - dp) + theta;
+            q = ((gamma - dp) + gamma) + dy;
+            r = p / q;
+            stpc = stp + r * (sty - stp);
+            stpf = stpc;
+        } else if (stp > stx) stpf = stpmax;
+        else stpf = stpmin;
+    }
+    if (fp > fx) {
+        sty = stp; fy = fp; dy = dp;
+    } else {
+        if (sgnd < 0.0) { sty = stx; fy = fx; dy = dx; }
+        stx = stp; fx = fp; dx = dp;
+    }
+    stp = stpf;
+}
+
+#define LS_FTOL 1e-3
+#define LS_GTOL 0.9
+#define LS_XTOL 0.1
+#define LS_STPMIN 0.0
+#define LS_STPMAX 1e10
+
+// returns false on "ERROR" (initial slope not negative / step out of range)
+__device__ __forceinline__ bool dcsrch_start(DcsrchState& s, double f, double g, double stp) {
+    if (stp < LS_STPMIN || stp > LS_STPMAX || !(g < 0.0)) return false;
+    s.brackt = false;
+    s.stage = 1;
+    s.finit = f; s.ginit = g;
+    s.gtest = LS_FTOL * g;
+    s.width = LS_STPMAX - LS_STPMIN;
+    s.width1 = s.width / 0.5;
+    s.stx = 0.0; s.fx = f; s.gx = g;
+    s.sty = 0.0; s.fy = f; s.gy = g;
+    s.stmin = 0.0;
+    s.stmax = stp + 4.0 * stp;
+    s.stp = stp;
+    return true;
+}
+
+// returns 0 = evaluate again at s.stp, 1 = converged, 2 = warning (also terminates the search)
+__device__ __forceinline__ int dcsrch_step(DcsrchState& s, double f, double g) {
+    double stp = s.stp;
+    const double ftest = s.finit + stp * s.gtest;
+    if (s.stage == 1 && f <= ftest && g >= 0.0) s.stage = 2;
+    int task = 0;
+    if (s.brackt && (stp <= s.stmin || stp >= s.stmax)) task = 2;
+    if (s.brackt && s.stmax - s.stmin <= LS_XTOL * s.stmax) task = 2;
+    if (stp == LS_STPMAX && f <= ftest && g <= s.gtest) task = 2;
+    if (stp == LS_STPMIN && (f > ftest || g >= s.gtest)) task = 2;
+    if (f <= ftest && fabs(g) <= LS_GTOL * (-s.ginit)) task = 1;
+    if (task != 0) return task;
+    if (s.stage == 1 && f <= s.fx && f > ftest) {
+        const double gt = s.gtest;
+        const double fm = f - stp * gt;
+        double fxm = s.fx - s.stx * gt, fym = s.fy - s.sty * gt;
+        const double gm = g - gt;
+        double gxm = s.gx - gt, gym = s.gy - gt;
+        dcstep(s.stx, fxm, gxm, s.sty, fym, gym, stp, fm, gm, s.brackt, s.stmin, s.stmax);
+        s.fx = fxm + s.stx * gt;
+        s.fy = fym + s.sty * gt;
+        s.gx = gxm + gt;
+        s.gy = gym + gt;
+    } else {
+        dcstep(s.stx, s.fx, s.gx, s.sty, s.fy, s.gy, stp, f, g, s.brackt, s.stmin, s.stmax);
+    }
+    if (s.brackt) {
+        if (fabs(s.sty - s.stx) >= 0.66 * s.width1) stp = s.stx + 0.5 * (s.sty - s.stx);
+        s.width1 = s.width;
+        s.width = fabs(s.sty - s.stx);
+    }
+    if (s.brackt) {
+        s.stmin = fmin(s.stx, s.sty);
+        s.stmax = fmax(s.stx, s.sty);
+    } else {
+        s.stmin = stp + 1.1 * (stp - s.stx);
+        s.stmax = stp + 4.0 * (stp - s.stx);
+    }
+    stp = fmax(stp, LS_STPMIN);
+    stp = fmin(stp, LS_STPMAX);
+    if ((s.brackt && (stp <= s.stmin || stp >= s.stmax)) || (s.brackt && s.stmax - s.stmin <= LS_XTOL * s.stmax))
+        stp = s.stx;
+    s.stp = stp;
+    return 0;
+}
+
+// Upper Cholesky A = R^T R of the leading n x n block (LINPACK dpofa); returns 0 or the failing pivot.
+__device__ int small_chol_upper(double* A, int lda, int n) {
+    for (int j = 0; j < n; ++j) {
+        double s = 0.0;
+        for (int k = 0; k < j; ++k) {
+            double t = A[k * lda + j];
+            for (int i = 0; i < k; ++i) t -= A[i * lda + k] * A[i * lda + j];
+            t /= A[k * lda + k];
+            A[k * lda + j] = t;
+            s += t * t;
+        }
+        s = A[j * lda + j] - s;
+        if (!(s > 0.0)) return j + 1;
+        A[j * lda + j] = sqrt(s);
+    }
+    return 0;
+}
+
+// formk for the all-free case, run by thread 0: builds and factors WN (upper triangle). 0 on success.
+__device__ int formk_free(OptSmem* os, int col, double theta) {
+    const int L2 = 2 * GPC_MMAX;
+    double* WN = &os->WN[0][0];
+    for (int iy = 0; iy < col; ++iy) {
+        for (int jy = 0; jy <= iy; ++jy) {
+            WN[jy * L2 + iy] = os->YY[iy][jy] / theta;                 // Y'Y / theta
+            WN[(col + jy) * L2 + col + iy] = 0.0;                      // theta * S'AA'S = 0 (no active bounds)
+        }
+        for (int jy = 0; jy < iy; ++jy) WN[jy * L2 + col + iy] = 0.0;  // -L_a' = 0
+        for (int jy = iy; jy < col; ++jy) WN[jy * L2 + col + iy] = os->RZ[iy][jy];   // R_z'
+        WN[iy * L2 + iy] += os->SY[iy][iy];                            // + D
+    }
+    int info = small_chol_upper(WN, L2, col);
+    if (info != 0) return -1;
+    // columns of block (1,2): solve R1^T x = b  (dtrsl job 11)
+    for (int js = col; js < 2 * col; ++js)
+        for (int i = 0; i < col; ++i) {
+            double t = WN[i * L2 + js];
+            for (int k = 0; k < i; ++k) t -= WN[k * L2 + i] * WN[k * L2 + js];
+            WN[i * L2 + js] = t / WN[i * L2 + i];
+        }
+    for (int is = col; is < 2 * col; ++is)
+        for (int js = is; js < 2 * col; ++js) {
+            double t = 0.0;
+            for (int k = 0; k < col; ++k) t += WN[k * L2 + is] * WN[k * L2 + js];
+            WN[is * L2 + js] += t;
+        }
+    info = small_chol_upper(WN + col * L2 + col, L2, col);
+    if (info != 0) return -2;
+    return 0;
+}
+
+// formt: T = theta*SS + L D^-1 L^T must be positive definite (thread 0). 0 on success.
+__device__ int formt_check(OptSmem* os, int col, double theta) {
+    double T[GPC_MMAX * GPC_MMAX];
+    for (int j = 0; j < col; ++j) T[j] = theta * os->SS[0][j];
+    for (int i = 1; i < col; ++i)
+        for (int j = i; j < col; ++j) {
+            const int k1 = min(i, j);
+            double ddum = 0.0;
+            for (int k = 0; k < k1; ++k) ddum += os->SY[i][k] * os->SY[j][k] / os->SY[k][k];
+            T[i * GPC_MMAX + j] = ddum + theta * os->SS[i][j];
+        }
+    return small_chol_upper(T, GPC_MMAX, col);
+}
+
+// subsm middle solve (thread 0): wv <- K^-1 wv through the LEL^T factor.
+__device__ void subsm_solve(OptSmem* os, int col) {
+    const int L2 = 2 * GPC_MMAX, c2 = 2 * col;
+    double* WN = &os->WN[0][0];
+    double* wv = os->wv;
+    for (int i = 0; i < c2; ++i) {                       // U^T x = b
+        double t = wv[i];
+        for (int k = 0; k < i; ++k) t -= WN[k * L2 + i] * wv[k];
+        wv[i] = t / WN[i * L2 + i];
+    }
+    for (int i = 0; i < col; ++i) wv[i] = -wv[i];
+    for (int i = c2 - 1; i >= 0; --i) {                  // U x = b
+        double t = wv[i];
+        for (int k = i + 1; k < c2; ++k) t -= WN[i * L2 + k] * wv[k];
+        wv[i] = t / WN[i * L2 + i];
+    }
+}
+
+struct OptResult {
+    int task;          // TASK_*
+    int nit, nfev;
+    double f;          // final loss (= -ELBO)
+    double gnorm;      // max |g|
+};
+
+__device__ __forceinline__ double cta_max(double v, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double t = red[0];
+#pragma unroll
+    for (int w = 1; w < GPC_THREADS / 32; ++w) t = fmax(t, red[w]);
+    __syncthreads();
+    return t;
+}
+
+// Evaluate loss = -ELBO and its gradient at ws.x; returns status. g is written negated into ws.g.
+__device__ __forceinline__ int eval_loss(const ModelDev& md, const double* Z, const double* y, const double* scale,
+                                         const SlotWs& ws, CtaSmem* sm, double& loss) {
+    double elbo;
+    const int st = model_eval(md, Z, y, scale, ws.x, ws.g, &elbo, ws, sm);
+    if (st != GPC_ST_OK) return st;
+    loss = -elbo;
+    return GPC_ST_OK;
+}
+
+// Minimise from ws.x (in/out). Memory slots: WS / WY rows of length P, slot (head + j) % m holds pair j.
+__device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const double* y, const double* scale,
+                                     const gpc_opt_t& opt, const SlotWs& ws, CtaSmem* sm, OptSmem* os) {
+    const int P = md.P, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m = opt.m;
+    OptResult res;
+    res.nit = 0; res.nfev = 0; res.task = TASK_ABNORMAL; res.f = NAN; res.gnorm = NAN;
+    double f;
+    if (eval_loss(md, Z, y, scale, ws, sm, f) != GPC_ST_OK) { res.task = TASK_CHOL; res.nfev = 1; return res; }
+    int nfev = 1, nit = 0;
+    // g <- -grad(ELBO)
+    double gmax = 0.0;
+    for (int i = tid; i < P; i += GPC_THREADS) { const double v = -ws.g[i]; ws.g[i] = v; gmax = fmax(gmax, fabs(v)); }
+    double sbgnrm = cta_max(gmax, sm->red);
+    if (sbgnrm <= opt.gtol) { res.task = TASK_PGTOL; res.nfev = nfev; res.f = f; res.gnorm = sbgnrm; return res; }
+    int col = 0, head = 0;
+    double theta = 1.0;
+    bool updated = false;      // a new pair was stored since the last formk
+    while (true) {
+        // ------------------------------------------------------------------ search direction
+        if (col == 0) {
+            for (int i = tid; i < P; i += GPC_THREADS) {
+                const double zi = ws.x[i] - ws.g[i] / theta;
+                ws.z[i] = zi;
+                ws.d[i] = zi - ws.x[i];
+            }
+        } else {
+            if (tid == 0) {
+                int info = 0;
+                if (updated) info = formk_free(os, col, theta);
+                if (info == 0) {
+                    for (int j = 0; j < col; ++j) {
+                        os->wv[j] = -os->dots[j][5];                 // Y_j . r, r = -g
+                        os->wv[col + j] = -theta * os->dots[j][4];   // theta * S_j . r
+                    }
+                    subsm_solve(os, col);
+                }
+                os->info = info;
+            }
+            __syncthreads();
+            const int info = os->info;
+            __syncthreads();
+            if (info != 0) { col = 0; head = 0; theta = 1.0; updated = false; continue; }   // refresh the memory
+            updated = false;
+            for (int i = tid; i < P; i += GPC_THREADS) {
+                double di = -ws.g[i];
+                for (int j = 0; j < col; ++j) {
+                    const size_t slot = (size_t)((head + j) % m) * P;
+                    di += ws.WY[slot + i] * (os->wv[j] / theta) + ws.WS[slot + i] * os->wv[col + j];
+                }
+                di *= 1.0 / theta;
+                const double zi = ws.x[i] + di;
+                ws.z[i] = zi;
+                ws.d[i] = zi - ws.x[i];
+            }
+        }
+        __syncthreads();
+        // ------------------------------------------------------------------ line search (lnsrlb)
+        double acc2[2] = {0.0, 0.0};
+        for (int i = tid; i < P; i += GPC_THREADS) {
+            const double di = ws.d[i];
+            acc2[0] = fma(di, di, acc2[0]);
+            acc2[1] = fma(ws.g[i], di, acc2[1]);
+            ws.xold[i] = ws.x[i];
+            ws.gold[i] = ws.g[i];
+        }
+        cta_sum_n<2>(acc2, sm->red);
+        const double dtd = acc2[0];
+        const double dnorm = sqrt(dtd);
+        double gd = acc2[1];
+        const double gdold = gd;
+        const double fold = f;
+        double stp = (nit == 0) ? fmin(1.0 / dnorm, LS_STPMAX) : 1.0;
+        bool ls_failed = false;
+        DcsrchState ls;
+        if (!(gd < 0.0) || !dcsrch_start(ls, f, gd, stp)) {
+            ls_failed = true;                      // ascent direction in projection (info = -4)
+        } else {
+            int ifun = 0;
+            while (true) {
+                stp = ls.stp;
+                ++ifun;
+                ++nfev;
+                if (stp == 1.0) {
+                    for (int i = tid; i < P; i += GPC_THREADS) ws.x[i] = ws.z[i];
+                } else {
+                    for (int i = tid; i < P; i += GPC_THREADS) ws.x[i] = stp * ws.d[i] + ws.xold[i];
+                }
+                __syncthreads();
+                if (eval_loss(md, Z, y, scale, ws, sm, f) != GPC_ST_OK) {
+                    res.task = TASK_CHOL; res.nit = nit; res.nfev = nfev; return res;
+                }
+                double a = 0.0;
+                for (int i = tid; i < P; i += GPC_THREADS) { const double v = -ws.g[i]; ws.g[i] = v; a = fma(v, ws.d[i], a); }
+                gd = cta_sum(a, sm->red);
+                const int t = dcsrch_step(ls, f, gd);
+                if (t != 0) break;
+                if (ifun >= opt.maxls) { ls_failed = true; break; }
+            }
+        }
+        if (ls_failed) {
+            for (int i = tid; i < P; i += GPC_THREADS) { ws.x[i] = ws.xold[i]; ws.g[i] = ws.gold[i]; }
+            f = fold;
+            __syncthreads();
+            if (col == 0) { res.task = TASK_ABNORMAL; ++nit; break; }
+            col = 0; head = 0; theta = 1.0; updated = false;
+            continue;
+        }
+        stp = ls.stp;
+        ++nit;
+        // ------------------------------------------------------------------ limits and convergence tests
+        gmax = 0.0;
+        for (int i = tid; i < P; i += GPC_THREADS) gmax = fmax(gmax, fabs(ws.g[i]));
+        sbgnrm = cta_max(gmax, sm->red);
+        if (nit >= opt.maxiter || nfev > opt.maxfun) { res.task = TASK_LIMIT; break; }
+        if (sbgnrm <= opt.gtol) { res.task = TASK_PGTOL; break; }
+        if ((fold - f) <= opt.ftol * fmax(fmax(fabs(fold), fabs(f)), 1.0)) { res.task = TASK_FTOL; break; }
+        // ------------------------------------------------------------------ BFGS update (matupd)
+        double rr = 0.0;
+        for (int i = tid; i < P; i += GPC_THREADS) {
+            const double r = ws.g[i] - ws.gold[i];
+            ws.gold[i] = r;
+            rr = fma(r, r, rr);
+        }
+        rr = cta_sum(rr, sm->red);
+        double dr, ddum;
+        if (stp == 1.0) {
+            dr = gd - gdold;
+            ddum = -gdold;
+        } else {
+            dr = (gd - gdold) * stp;
+            for (int i = tid; i < P; i += GPC_THREADS) ws.d[i] *= stp;
+            ddum = -gdold * stp;
+        }
+        const bool skip = dr <= GPC_EPSMCH * ddum;
+        if (!skip) {
+            if (col == m) {       // drop the oldest pair: shift the small matrices
+                __syncthreads();
+                if (tid == 0) {
+                    for (int i = 0; i < m - 1; ++i)
+                        for (int j = 0; j < m - 1; ++j) {
+                            os->SS[i][j] = os->SS[i + 1][j + 1];
+                            os->SY[i][j] = os->SY[i + 1][j + 1];
+                            os->YY[i][j] = os->YY[i + 1][j + 1];
+                            os->RZ[i][j] = os->RZ[i + 1][j + 1];
+                        }
+                }
+                head = (head + 1) % m;
+                col = m - 1;
+            }
+            const size_t slot = (size_t)((head + col) % m) * P;
+            for (int i = tid; i < P; i += GPC_THREADS) { ws.WS[slot + i] = ws.d[i]; ws.WY[slot + i] = ws.gold[i]; }
+            ++col;
+            theta = rr / dr;
+            updated = true;
+        }
+        __syncthreads();
+        // dots of every memory pair with the new s (= d), y (= gold) and the new gradient g
+        for (int j = warp; j < col; j += GPC_THREADS / 32) {
+            const size_t slot = (size_t)((head + j) % m) * P;
+            double a[6] = {0, 0, 0, 0, 0, 0};
+            for (int i = lane; i < P; i += 32) {
+                const double s = ws.WS[slot + i], yv = ws.WY[slot + i];
+                const double di = ws.d[i], ri = ws.gold[i], gi = ws.g[i];
+                a[0] = fma(s, di, a[0]); a[1] = fma(yv, di, a[1]);
+                a[2] = fma(s, ri, a[2]); a[3] = fma(yv, ri, a[3]);
+                a[4] = fma(s, gi, a[4]); a[5] = fma(yv, gi, a[5]);
+            }
+#pragma unroll
+            for (int q = 0; q < 6; ++q) a[q] = warp_sum(a[q]);
+            if (lane == 0)
+                for (int q = 0; q < 6; ++q) os->dots[j][q] = a[q];
+        }
+        __syncthreads();
+        if (!skip && tid == 0) {
+            const int c = col - 1;
+            for (int j = 0; j < col; ++j) {
+                os->SS[j][c] = os->SS[c][j] = os->dots[j][0];
+                os->YY[j][c] = os->YY[c][j] = os->dots[j][3];
+                os->SY[c][j] = os->dots[j][1];        // s_new . y_j
+                os->RZ[j][c] = os->dots[j][2];        // s_j . y_new (diagonal included)
+            }
+            os->SS[c][c] = (stp == 1.0) ? dtd : stp * stp * dtd;
+            os->SY[c][c] = dr;
+            os->info = formt_check(os, col, theta);
+        }
+        __syncthreads();
+        if (!skip) {
+            const int info = os->info;
+            __syncthreads();
+            if (info != 0) { col = 0; head = 0; theta = 1.0; updated = false; }
+        }
+    }
+    res.nit = nit;
+    res.nfev = nfev;
+    res.f = f;
+    res.gnorm = sbgnrm;
+    return res;
+}

@@ -1,0 +1,142 @@
+// Likelihood terms of the variational expectations: 20-point Gauss-Hermite quadrature of the NB / ZINB
+// log-densities (GPcounts/NegativeBinomialLikelihood.py:37-48, 63-77), the Poisson closed form
+// (gpflow.likelihoods.Poisson, GPcounts_Module.py:622-623), with the analytic derivatives
+// d/d(fmean), d/d(fvar), d/d(alpha), d/d(km) that the reference obtains from TensorFlow autodiff.
+#pragma once
+#include <math.h>
+#include "../../include/gpcounts_b200.h"
+
+#define GPC_NGH 20
+
+// numpy.polynomial.hermite.hermgauss(20): nodes * sqrt(2), weights / sqrt(pi)
+__constant__ double c_gh_z[GPC_NGH];
+__constant__ double c_gh_w[GPC_NGH];
+
+struct LikParams {
+    int lik;
+    double alpha, km;       // constrained values
+    double k;               // 1 / alpha
+    double log_alpha;
+    double lgamma_k;        // lgamma(k)
+    double digamma_k;       // psi(k)
+};
+
+struct LikPoint {
+    double ve;              // E_q[log p(y|f)]
+    double gm;              // d ve / d fmean
+    double gv;              // d ve / d fvar
+    double dalpha;          // d ve / d alpha
+    double dkm;             // d ve / d km
+};
+
+// psi(x), x > 0: upward recurrence to x >= 10, then the asymptotic series (error < 1e-15).
+__device__ __forceinline__ double digamma_pos(double x) {
+    double r = 0.0;
+    while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
+    const double xi = 1.0 / x, x2 = xi * xi;
+    double s = x2 * (1.0 / 12.0 - x2 * (1.0 / 120.0 - x2 * (1.0 / 252.0 - x2 * (1.0 / 240.0 - x2 * (1.0 / 132.0
+               - x2 * (691.0 / 32760.0 - x2 * (1.0 / 12.0)))))));
+    return r + log(x) - 0.5 * xi - s;
+}
+
+__device__ __forceinline__ void lik_setup(LikParams& lp, int lik, double alpha, double km) {
+    lp.lik = lik;
+    lp.alpha = alpha;
+    lp.km = km;
+    lp.k = 1.0 / alpha;
+    lp.log_alpha = log(alpha);
+    lp.lgamma_k = lgamma(lp.k);
+    lp.digamma_k = digamma_pos(lp.k);
+}
+
+// y: count, s: scale factor (1 if none), lgy1 = lgamma(y + 1)
+__device__ LikPoint lik_point(const LikParams& lp, double fm, double fv, double y, double s) {
+    LikPoint o;
+    o.dalpha = 0.0;
+    o.dkm = 0.0;
+    if (lp.lik == GPC_POISSON) {
+        const double e = exp(fm + 0.5 * fv);
+        o.ve = y * fm - e - lgamma(y + 1.0);
+        o.gm = y - e;
+        o.gv = -0.5 * e;
+        return o;
+    }
+    const double sd = sqrt(fv);
+    const double alpha = lp.alpha, k = lp.k;
+    const double ia = k, ia2 = k * k;
+    double ve = 0.0, gm = 0.0, gz = 0.0, da = 0.0, dk = 0.0;
+    if (lp.lik == GPC_NB) {
+        const double logs = log(s);
+#pragma unroll 4
+        for (int i = 0; i < GPC_NGH; ++i) {
+            const double z = c_gh_z[i], w = c_gh_w[i];
+            const double logm = fm + sd * z + logs;
+            const double m = exp(logm);
+            const double t = 1.0 + m * alpha;
+            const double lt = log(t);
+            const double l = y * (logm + lp.log_alpha - lt) - k * lt;
+            const double dl = (y - m) / t;
+            const double dal = y * ia + lt * ia2 - (y + k) * m / t;
+            ve = fma(w, l, ve);
+            gm = fma(w, dl, gm);
+            gz = fma(w * z, dl, gz);
+            da = fma(w, dal, da);
+        }
+        const double dpsi = digamma_pos(k + y) - lp.digamma_k;
+        ve += lgamma(k + y) - lgamma(y + 1.0) - lp.lgamma_k;
+        da += -ia2 * dpsi;
+    } else {  // GPC_ZINB (no scale in the reference)
+        const double km = lp.km;
+        if (y == 0.0) {
+#pragma unroll 2
+            for (int i = 0; i < GPC_NGH; ++i) {
+                const double z = c_gh_z[i], w = c_gh_w[i];
+                const double F = fm + sd * z;
+                const double m = exp(F);
+                const double t = 1.0 + m * alpha;
+                const double lt = log(t);
+                const double kmm = km + m;
+                const double psi0 = km / kmm;
+                const double a = log(psi0);
+                const double b = F - log(kmm) - lt * ia;
+                const double mx = fmax(a, b);
+                const double ea = exp(a - mx), eb = exp(b - mx);
+                const double se = ea + eb;
+                const double l = mx + log(se);
+                const double ra = ea / se, rb = eb / se;
+                const double dl = -ra * (1.0 - psi0) + rb * (psi0 - m / t);
+                ve = fma(w, l, ve);
+                gm = fma(w, dl, gm);
+                gz = fma(w * z, dl, gz);
+                dk = fma(w, ra * m / (km * kmm) - rb / kmm, dk);
+                da = fma(w, rb * (lt * ia2 - m * ia / t), da);
+            }
+        } else {
+#pragma unroll 2
+            for (int i = 0; i < GPC_NGH; ++i) {
+                const double z = c_gh_z[i], w = c_gh_w[i];
+                const double F = fm + sd * z;
+                const double m = exp(F);
+                const double t = 1.0 + m * alpha;
+                const double lt = log(t);
+                const double kmm = km + m;
+                const double l = (F - log(kmm)) + y * (F + lp.log_alpha - lt) - k * lt;
+                const double dl = km / kmm + (y - m) / t;
+                ve = fma(w, l, ve);
+                gm = fma(w, dl, gm);
+                gz = fma(w * z, dl, gz);
+                dk = fma(w, -1.0 / kmm, dk);
+                da = fma(w, y * ia + lt * ia2 - (y + k) * m / t, da);
+            }
+            const double dpsi = digamma_pos(k + y) - lp.digamma_k;
+            ve += lgamma(k + y) - lgamma(y + 1.0) - lp.lgamma_k;
+            da += -ia2 * dpsi;
+        }
+    }
+    o.ve = ve;
+    o.gm = gm;
+    o.gv = gz / (2.0 * sd);
+    o.dalpha = da;
+    o.dkm = dk;
+    return o;
+}

@@ -1,0 +1,104 @@
+"""Fixed-theta parity: ELBO and gradient of the CUDA path vs the CPU oracle, tolerance 1e-8 relative
+(BASELINE.json north_star), for every model x kernel x likelihood variant of the hot path."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import random_theta, synth_counts
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-8
+
+
+def _compare(kind, kernel, lik, N, M=0, d=1, use_scale=False, D=3, seed=0, train=(True, True, True, True), xp=None):
+    from gpcounts_b200 import engine
+    from oracle import gp_math as gm
+    rng = np.random.default_rng(seed)
+    X, Y = synth_counts(D, N, seed=seed + 10)
+    if d == 2:
+        X = np.c_[X, rng.uniform(0, 1, N)]
+    if kernel == "BRANCH":
+        X = np.c_[X[:, 0], rng.integers(1, 3, N).astype(float)]
+        xpv = 0.4 if xp is None else xp
+        X[X[:, 0] <= xpv, 1] = 1.0
+    else:
+        xpv = -1000.0
+    Z = None
+    if kind in ("SVGP", "SGPR"):
+        Z = X[np.sort(rng.choice(N, M, replace=False))].copy()
+    if lik == "GAUSS":
+        Y = np.log(Y + 1)
+    scale = rng.uniform(0.5, 2.0, (D, N)) if use_scale else None
+    spec = gm.ModelSpec(kind=kind, kernel=kernel, lik=lik, X=X, Z=Z, xp=xpv, train=train)
+    theta = random_theta(spec, rng, D)
+    model = engine.Model(kind, kernel, lik, X, Z=Z, train=train, xp=xpv)
+    elbo, grad, status = engine.elbo_grad(model, Y, scale, theta)
+    elbo, grad, status = elbo.cpu().numpy(), grad.cpu().numpy(), status.cpu().numpy()
+    assert (status == 0).all()
+    for g in range(D):
+        f_ref, g_ref = gm.elbo_and_grad(theta[g], spec, Y[g], None if scale is None else scale[g])
+        assert abs(elbo[g] - f_ref) <= TOL * abs(f_ref), (g, elbo[g], f_ref)
+        # gradient blocks are compared on the scale of the largest entry of each block
+        mv = spec.Mv
+        blocks = [slice(0, 4), slice(4, 4 + mv), slice(4 + mv, spec.P)] if mv else [slice(0, 4)]
+        for b in blocks:
+            ref = g_ref[b]
+            if ref.size == 0:
+                continue
+            err = np.abs(grad[g][b] - ref).max() / max(np.abs(ref).max(), 1e-300)
+            assert err <= TOL, (kind, kernel, lik, g, b, err)
+
+
+@pytest.mark.parametrize("lik", ["NB", "ZINB", "POISSON"])
+@pytest.mark.parametrize("kernel", ["RBF", "CONST"])
+def test_svgp(lik, kernel):
+    _compare("SVGP", kernel, lik, N=150, M=20)
+
+
+@pytest.mark.parametrize("lik", ["NB", "ZINB", "POISSON"])
+@pytest.mark.parametrize("kernel", ["RBF", "CONST"])
+def test_vgp(lik, kernel):
+    _compare("VGP", kernel, lik, N=40)
+
+
+def test_vgp_blocked_sizes():
+    _compare("VGP", "RBF", "NB", N=130, D=2)        # three 64-blocks, ragged last
+
+
+def test_svgp_blocked_sizes():
+    _compare("SVGP", "RBF", "NB", N=300, M=70, D=2)
+
+
+def test_svgp_scale_2d():
+    _compare("SVGP", "RBF", "NB", N=120, M=16, d=2, use_scale=True)
+
+
+def test_vgp_scale_2d():
+    _compare("VGP", "RBF", "NB", N=60, d=2, use_scale=True)
+
+
+@pytest.mark.parametrize("xp", [-1000.0, 0.4])
+def test_vgp_branch(xp):
+    _compare("VGP", "BRANCH", "NB", N=50, xp=xp)
+
+
+def test_vgp_branch_frozen_kernel():
+    _compare("VGP", "BRANCH", "NB", N=50, xp=0.4, train=(False, False, True, True))
+
+
+@pytest.mark.parametrize("kernel", ["RBF", "CONST"])
+def test_gpr(kernel):
+    _compare("GPR", kernel, "GAUSS", N=70)
+
+
+def test_not_positive_definite_is_reported():
+    from gpcounts_b200 import engine
+    from oracle import gp_math as gm
+    X, Y = synth_counts(2, 30)
+    spec = gm.ModelSpec(kind="VGP", kernel="RBF", lik="NB", X=X)
+    theta = random_theta(spec, np.random.default_rng(0), 2)
+    theta[1, 0] = float("nan")
+    model = engine.Model("VGP", "RBF", "NB", X)
+    elbo, grad, status = engine.elbo_grad(model, Y, None, theta)
+    assert status.tolist() == [0, 1]
+    assert torch.isnan(elbo[1]) and torch.isfinite(elbo[0])
