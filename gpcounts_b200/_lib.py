@@ -24,7 +24,7 @@ class gpc_model_t(C.Structure):
         ("kind", C.c_int32), ("kernel", C.c_int32), ("lik", C.c_int32), ("N", C.c_int32), ("M", C.c_int32),
         ("d", C.c_int32), ("n_off", C.c_int32), ("train_mask", C.c_int32), ("n_zsets", C.c_int32),
         ("handoff_alpha", C.c_int32), ("xp", C.c_double), ("jitter", C.c_double),
-        ("X", C.c_void_p), ("Z", C.c_void_p), ("restart", C.c_void_p),
+        ("X", C.c_void_p), ("Z", C.c_void_p), ("Zgene", C.c_void_p), ("restart", C.c_void_p),
     ]
 
 
@@ -34,7 +34,7 @@ class gpc_opt_t(C.Structure):
 
 
 EXPORTS = ["gpc_default_opt", "gpc_param_count", "gpc_default_slots", "gpc_workspace_bytes", "gpc_elbo_grad",
-           "gpc_fit", "gpc_dbg_linalg", "gpc_launch_count", "gpc_last_error_string", "gpc_version"]
+           "gpc_fit", "gpc_dbg_linalg", "gpc_dbg_set_trace", "gpc_launch_count", "gpc_last_error_string", "gpc_version"]
 
 _lib = None
 
@@ -69,6 +69,8 @@ def load():
     lib.gpc_dbg_linalg.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p]
     lib.gpc_dbg_linalg.restype = C.c_int
+    lib.gpc_dbg_set_trace.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+    lib.gpc_dbg_set_trace.restype = None
     lib.gpc_launch_count.argtypes = []
     lib.gpc_launch_count.restype = C.c_int64
     lib.gpc_last_error_string.argtypes = []

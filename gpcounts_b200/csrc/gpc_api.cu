@@ -12,6 +12,8 @@
 #include "lbfgsb.cuh"
 
 static thread_local char g_err[512] = "";
+static double* g_trace = nullptr;
+static int g_trace_cap = 0, g_trace_gene = 0, g_trace_model = 0;
 static long long g_launches = 0;
 
 static int set_err(int code, const char* fmt, const char* a = "") {
@@ -74,7 +76,7 @@ __host__ __device__ static inline ModelDev to_dev(const gpc_model_t& md) {
     ModelDev d;
     d.kind = md.kind; d.kernel = md.kernel; d.lik = md.lik; d.N = md.N; d.M = md.M; d.d = md.d;
     d.n_off = md.n_off; d.train_mask = md.train_mask; d.n_zsets = md.n_zsets; d.handoff_alpha = md.handoff_alpha;
-    d.xp = md.xp; d.jitter = md.jitter; d.X = md.X; d.Z = md.Z; d.restart = md.restart;
+    d.xp = md.xp; d.jitter = md.jitter; d.X = md.X; d.Z = md.Z; d.Zgene = md.Zgene; d.restart = md.restart;
     d.Mv = md.kind == GPC_VGP ? md.N : (md.kind == GPC_SVGP ? md.M : 0);
     d.P = GPC_NHYP + d.Mv + d.Mv * (d.Mv + 1) / 2;
     return d;
@@ -92,6 +94,8 @@ struct FitArgs {
     double* ws;
     int* queue;
     WsLayout lay;
+    double* trace;            // debug: evaluation trace of (trace_gene, trace_model), 8 doubles per evaluation
+    int trace_cap, trace_gene, trace_model;
 };
 
 extern __shared__ __align__(16) unsigned char g_smem[];
@@ -134,7 +138,10 @@ __device__ bool fit_one(const FitArgs& a, int g, int k, double prev_alpha, const
         for (int i = tid; i < md.Mv; i += GPC_THREADS) ws.x[GPC_NHYP + md.Mv + tri_index(i, i)] = 1.0;
         __syncthreads();
         const double* Z = md.Z ? md.Z + (size_t)(md.n_zsets > 1 ? attempt : 0) * md.M * md.d : nullptr;
-        r = lbfgsb_minimize(md, Z, y, scale, a.opt, ws, sm, os);
+        if (attempt == 0 && md.Zgene) Z = md.Zgene + (size_t)g * md.M * md.d;
+        OptTrace tr{nullptr, 0, 0};
+        if (a.trace && g == a.trace_gene && k == a.trace_model && attempt == 0) { tr.buf = a.trace; tr.cap = a.trace_cap; }
+        r = lbfgsb_minimize(md, Z, y, scale, a.opt, ws, sm, os, &tr);
         nfev_total += r.nfev;
         ok = (r.task == TASK_PGTOL || r.task == TASK_FTOL);
         if (ok || attempt >= max_restart) break;
@@ -224,6 +231,7 @@ __global__ void __launch_bounds__(GPC_THREADS) k_elbo_grad(EvalArgs a) {
         const double* y = a.Y + (size_t)g * a.ldy + md.n_off;
         const double* scale = a.scale ? a.scale + (size_t)g * a.ldy + md.n_off : nullptr;
         const double* Z = md.Z ? md.Z + (size_t)a.zset * md.M * md.d : nullptr;
+        if (md.Zgene) Z = md.Zgene + (size_t)g * md.M * md.d;
         double* grad = a.grad + (size_t)g * md.P;
         double f;
         const int st = model_eval(md, Z, y, scale, a.theta + (size_t)g * md.P, grad, &f, ws, sm);
@@ -331,7 +339,7 @@ int32_t gpc_default_slots(const gpc_model_t* models, int32_t n_models) {
 
 size_t gpc_workspace_bytes(const gpc_model_t* models, int32_t n_models, const gpc_opt_t* opt, int32_t n_slots) {
     const WsLayout L = make_layout(models, n_models, opt ? opt->m : 0);
-    return 256 + (size_t)n_slots * L.slot * sizeof(double);
+    return 256 + pad8(sizeof(ModelDev) * (size_t)n_models) + (size_t)n_slots * L.slot * sizeof(double);
 }
 
 int gpc_elbo_grad(const gpc_model_t* model, int32_t D, const double* Y, const double* scale, int64_t ldy,
@@ -398,6 +406,7 @@ int gpc_fit(const gpc_model_t* models, int32_t n_models, int32_t chain, const gp
     a.queue = (int*)workspace;
     a.ws = (double*)((char*)workspace + hdr);
     a.lay = L;
+    a.trace = g_trace; a.trace_cap = g_trace_cap; a.trace_gene = g_trace_gene; a.trace_model = g_trace_model;
     cudaMemsetAsync(a.queue, 0, 256, s);
     const int n_jobs = chain ? D : D * n_models;
     const int grid = n_slots < n_jobs ? n_slots : n_jobs;
@@ -423,6 +432,10 @@ int gpc_dbg_linalg(int32_t op, int32_t batch, int32_t n, int32_t nrhs, double* A
     cudaFree(scratch);
     if (e != cudaSuccess) return set_err(GPC_E_LAUNCH, "gpc_dbg_linalg: %s", cudaGetErrorString(e));
     return 0;
+}
+
+void gpc_dbg_set_trace(double* buf, int32_t cap, int32_t gene, int32_t model) {
+    g_trace = buf; g_trace_cap = cap; g_trace_gene = gene; g_trace_model = model;
 }
 
 int64_t gpc_launch_count(void) { return g_launches; }

@@ -282,6 +282,28 @@ __device__ __forceinline__ double cta_max(double v, double* red) {
     return t;
 }
 
+// Optional evaluation trace (debug hook, see gpc_dbg_set_trace): 8 doubles per evaluation.
+struct OptTrace {
+    double* buf;
+    int cap;
+    int n;
+};
+
+__device__ __forceinline__ void trace_eval(OptTrace* tr, double f, double stp, double gd, const double* x,
+                                           const double* g, int P, double* red) {
+    if (!tr || !tr->buf) return;
+    double gmax = 0.0;
+    int nan = 0;
+    for (int i = threadIdx.x; i < P; i += GPC_THREADS) { const double v = fabs(g[i]); if (v != v) nan = 1; else gmax = fmax(gmax, v); }
+    gmax = cta_max(gmax, red);
+    const double nn = cta_sum((double)nan, red);
+    if (threadIdx.x == 0 && tr->n < tr->cap) {
+        double* r = tr->buf + (size_t)tr->n * 8;
+        r[0] = f; r[1] = stp; r[2] = gd; r[3] = gmax; r[4] = x[0]; r[5] = x[1]; r[6] = x[2] ; r[7] = nn > 0 ? -x[3] - 1e300 : x[3];
+    }
+    tr->n += 1;
+}
+
 // Evaluate loss = -ELBO and its gradient at ws.x; returns status. g is written negated into ws.g.
 __device__ __forceinline__ int eval_loss(const ModelDev& md, const double* Z, const double* y, const double* scale,
                                          const SlotWs& ws, CtaSmem* sm, double& loss) {
@@ -294,7 +316,8 @@ __device__ __forceinline__ int eval_loss(const ModelDev& md, const double* Z, co
 
 // Minimise from ws.x (in/out). Memory slots: WS / WY rows of length P, slot (head + j) % m holds pair j.
 __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const double* y, const double* scale,
-                                     const gpc_opt_t& opt, const SlotWs& ws, CtaSmem* sm, OptSmem* os) {
+                                     const gpc_opt_t& opt, const SlotWs& ws, CtaSmem* sm, OptSmem* os,
+                                     OptTrace* tr = nullptr) {
     const int P = md.P, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m = opt.m;
     OptResult res;
@@ -302,6 +325,7 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
     double f;
     if (eval_loss(md, Z, y, scale, ws, sm, f) != GPC_ST_OK) { res.task = TASK_CHOL; res.nfev = 1; return res; }
     int nfev = 1, nit = 0;
+    trace_eval(tr, f, 0.0, 0.0, ws.x, ws.g, P, sm->red);
     // g <- -grad(ELBO)
     double gmax = 0.0;
     for (int i = tid; i < P; i += GPC_THREADS) { const double v = -ws.g[i]; ws.g[i] = v; gmax = fmax(gmax, fabs(v)); }
@@ -387,6 +411,7 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
                 double a = 0.0;
                 for (int i = tid; i < P; i += GPC_THREADS) { const double v = -ws.g[i]; ws.g[i] = v; a = fma(v, ws.d[i], a); }
                 gd = cta_sum(a, sm->red);
+                trace_eval(tr, f, stp, gd, ws.x, ws.g, P, sm->red);
                 const int t = dcsrch_step(ls, f, gd);
                 if (t != 0) break;
                 if (ifun >= opt.maxls) { ls_failed = true; break; }

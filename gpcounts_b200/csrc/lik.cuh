@@ -86,7 +86,14 @@ __device__ LikPoint lik_point(const LikParams& lp, double fm, double fv, double 
         ve += lgamma(k + y) - lgamma(y + 1.0) - lp.lgamma_k;
         da += -ia2 * dpsi;
     } else {  // GPC_ZINB (no scale in the reference)
+        // The dropout probability is formed exactly as the reference forms it, psi = 1 - m/(km+m)
+        // (NegativeBinomialLikelihood.py:69), including its cancellation when km << m.  When psi rounds to
+        // exactly 0 the reference's autodiff gradient is NaN for every parameter upstream of psi (the
+        // 0 * (1/psi) of d log(psi), for zero and non-zero counts alike because tf.where still back-propagates
+        // through the unselected branch); SciPy's line search then retreats to the current iterate and
+        // stops there with "success".  That behaviour decides where reference fits end, so it is kept.
         const double km = lp.km;
+        bool poison = false;
         if (y == 0.0) {
 #pragma unroll 2
             for (int i = 0; i < GPC_NGH; ++i) {
@@ -96,19 +103,24 @@ __device__ LikPoint lik_point(const LikParams& lp, double fm, double fv, double 
                 const double t = 1.0 + m * alpha;
                 const double lt = log(t);
                 const double kmm = km + m;
-                const double psi0 = km / kmm;
-                const double a = log(psi0);
-                const double b = F - log(kmm) - lt * ia;
+                const double q = m / kmm;
+                const double psi = 1.0 - q;
+                const double omp = 1.0 - psi;
+                poison = poison || (psi == 0.0);
+                const double a = log(psi);
+                const double b = log(omp) - lt * ia;
                 const double mx = fmax(a, b);
                 const double ea = exp(a - mx), eb = exp(b - mx);
                 const double se = ea + eb;
                 const double l = mx + log(se);
                 const double ra = ea / se, rb = eb / se;
-                const double dl = -ra * (1.0 - psi0) + rb * (psi0 - m / t);
+                const double dq = q * (km / kmm);                  // dq/dF
+                const double dqk = m / (kmm * kmm);                // -dq/dkm
+                const double dl = -ra * dq / psi + rb * (dq / omp - m / t);
                 ve = fma(w, l, ve);
                 gm = fma(w, dl, gm);
                 gz = fma(w * z, dl, gz);
-                dk = fma(w, ra * m / (km * kmm) - rb / kmm, dk);
+                dk = fma(w, ra * dqk / psi - rb * dqk / omp, dk);
                 da = fma(w, rb * (lt * ia2 - m * ia / t), da);
             }
         } else {
@@ -120,18 +132,23 @@ __device__ LikPoint lik_point(const LikParams& lp, double fm, double fv, double 
                 const double t = 1.0 + m * alpha;
                 const double lt = log(t);
                 const double kmm = km + m;
-                const double l = (F - log(kmm)) + y * (F + lp.log_alpha - lt) - k * lt;
-                const double dl = km / kmm + (y - m) / t;
+                const double q = m / kmm;
+                const double psi = 1.0 - q;
+                const double omp = 1.0 - psi;
+                poison = poison || (psi == 0.0);
+                const double l = log(omp) + y * (F + lp.log_alpha - lt) - k * lt;
+                const double dl = q * (km / kmm) / omp + (y - m) / t;
                 ve = fma(w, l, ve);
                 gm = fma(w, dl, gm);
                 gz = fma(w * z, dl, gz);
-                dk = fma(w, -1.0 / kmm, dk);
+                dk = fma(w, -(m / (kmm * kmm)) / omp, dk);
                 da = fma(w, y * ia + lt * ia2 - (y + k) * m / t, da);
             }
             const double dpsi = digamma_pos(k + y) - lp.digamma_k;
             ve += lgamma(k + y) - lgamma(y + 1.0) - lp.lgamma_k;
             da += -ia2 * dpsi;
         }
+        if (poison) { gm = NAN; gz = NAN; dk = NAN; }
     }
     o.ve = ve;
     o.gm = gm;

@@ -17,7 +17,7 @@
 struct ModelDev {
     int kind, kernel, lik, N, M, d, n_off, train_mask, n_zsets, handoff_alpha;
     double xp, jitter;
-    const double *X, *Z, *restart;
+    const double *X, *Z, *Zgene, *restart;
     int Mv;          // rows of q_mu / q_sqrt
     int P;           // parameter count
 };

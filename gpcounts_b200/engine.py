@@ -27,7 +27,7 @@ class Model:
     """One model of the per-gene chain; owns the device copies of X / Z / restart table it points to."""
 
     def __init__(self, kind, kernel, lik, X, Z=None, n_off=0, train=(True, True, True, True), handoff_alpha=False,
-                 xp=-1000.0, jitter=1e-6, restart=None, device="cuda"):
+                 xp=-1000.0, jitter=1e-6, restart=None, Zgene=None, device="cuda"):
         self.kind, self.kernel, self.lik = kind, kernel, lik
         X = np.asarray(X, dtype=np.float64)
         self.X = _dev_f64(X.reshape(X.shape[0], -1), device)
@@ -41,6 +41,7 @@ class Model:
             self.Z = _dev_f64(Z, device)            # (n_zsets, M, d)
             self.n_zsets, self.M = Z.shape[0], Z.shape[1]
         self.restart = _dev_f64(restart, device)    # (10, 4) = (ls, var, alpha, km) or None
+        self.Zgene = _dev_f64(Zgene, device)        # (D, M, d) per-gene inducing points of attempt 0, or None
         self.n_off = int(n_off)
         self.train_mask = sum(1 << i for i, t in enumerate(train) if t)
         self.handoff_alpha = bool(handoff_alpha)
@@ -63,6 +64,7 @@ class Model:
         m.xp, m.jitter = self.xp, self.jitter
         m.X = self.X.data_ptr()
         m.Z = self.Z.data_ptr() if self.Z is not None else None
+        m.Zgene = self.Zgene.data_ptr() if self.Zgene is not None else None
         m.restart = self.restart.data_ptr() if self.restart is not None else None
         return m
 

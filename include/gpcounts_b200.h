@@ -80,6 +80,9 @@ typedef struct gpc_model {
     double jitter;         /* gpflow default_jitter() = 1e-6                                     */
     const double* X;       /* device, N x d row-major                                            */
     const double* Z;       /* device, n_zsets x M x d, or NULL                                   */
+    const double* Zgene;   /* device, D x M x d per-gene inducing points for the first attempt, or NULL (then set 0 of Z).
+                              RobustGP's greedy selection runs under the gene's own initial variance (:673-677) and its
+                              near-ties are decided by rounding, so attempt 0 can have gene-specific Z.       */
     const double* restart; /* device, GPC_MAX_RESTART x 4 (ls, var, alpha, km) restart table (:769-779), or NULL = no restarts */
 } gpc_model_t;
 
@@ -146,6 +149,10 @@ int gpc_fit(const gpc_model_t* models, int32_t n_models, int32_t chain, const gp
  */
 int gpc_dbg_linalg(int32_t op, int32_t batch, int32_t n, int32_t nrhs, double* A, double* B, int32_t* status,
                    void* stream);
+
+/* Debug hook: record (loss, step, slope, max|g|, theta[0..3]) of every evaluation of attempt 0 of (gene, model)
+ * during subsequent gpc_fit calls into buf (device, cap x 8 doubles); buf = NULL switches it off. */
+void gpc_dbg_set_trace(double* buf, int32_t cap, int32_t gene, int32_t model);
 
 /* Number of kernel launches issued by this library since load (bench.py `gpu_launches`). */
 int64_t gpc_launch_count(void);

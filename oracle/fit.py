@@ -38,10 +38,15 @@ class FitResult:
         return dict(var=p[0], ls=p[1], alpha=p[2], km=p[3])
 
 
+PERTURB = 0.0     # test knob: relative size of a random perturbation of the start point (stability probes)
+
+
 def minimize_lbfgsb(spec, theta0, y, scale, options=None):
     """One ``gpflow.optimizers.Scipy().minimize`` call on the trainable variables."""
     idx = spec.trainable_index()
     theta = np.array(theta0, dtype=np.float64)
+    if PERTURB:
+        theta[idx] += PERTURB * np.random.default_rng(12345).standard_normal(idx.size)
 
     def fun(x):
         theta[idx] = x
@@ -59,7 +64,8 @@ def minimize_lbfgsb(spec, theta0, y, scale, options=None):
 class OracleFit:
     """Numpy-array analogue of ``Fit_GPcounts``: X (N,d), Y (D,N), scale (N,D) or None."""
 
-    def __init__(self, X, Y, scale=None, sparse=False, M=0, alpha_policy="handoff", lbfgs_options=None):
+    def __init__(self, X, Y, scale=None, sparse=False, M=0, alpha_policy="handoff", lbfgs_options=None,
+                 inducing_variance=None):
         self.X = np.asarray(X, dtype=np.float64).reshape(len(X), -1)
         self.Y = np.asarray(Y, dtype=np.float64)
         self.scale = None if scale is None else np.asarray(scale, dtype=np.float64)
@@ -71,6 +77,12 @@ class OracleFit:
         self.transform = True
         self.alpha_policy = alpha_policy    # "handoff" = Fit_GPcounts (:785-787); "one" = notebook goldens
         self.lbfgs_options = lbfgs_options
+        # RobustGP's greedy selection ties to the last bit while the inducing set is sparse, and the winner then
+        # depends on how (var0_g + 1e-12) - e^2 rounds (and on the BLAS summation order of its dot product): the
+        # reference's Z is not reproducible across machines at that level.  None = the gene's own initial
+        # variance as in the reference (:673-677); a number = use it for attempt 0 (fixes the tie-break so two
+        # implementations can be compared on identical Z).
+        self.inducing_variance = inducing_variance
         self.branching = False
         self.fix = False
         self.xp = -1000.0
@@ -129,7 +141,8 @@ class OracleFit:
                 alpha = 1.0                         # gpflow Gaussian likelihood default variance
             Z = None
             if self.sparse:                                                              # :655-659, 673-677
-                Z = select_Z(X, self.M, kernel, var, ls)
+                zvar = var if (self.inducing_variance is None or count_fix > 0) else self.inducing_variance
+                Z = select_Z(X, self.M, kernel, zvar, ls)
             kind = {(False, False): "VGP", (True, False): "SVGP",
                     (False, True): "GPR", (True, True): "SGPR"}[(self.sparse, lik == "GAUSS")]
             spec = ModelSpec(kind=kind, kernel=kernel, lik=lik, X=X, Z=Z, xp=xp, train=train)

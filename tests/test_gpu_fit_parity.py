@@ -1,0 +1,164 @@
+"""Optimised-fit parity through the drop-in API: ``Fit_GPcounts`` on the GPU vs the golden fixtures the CPU
+oracle produced (``tests/golden/make_fixtures.py``; SciPy L-BFGS-B from identical initialisation).
+
+Tolerances (BASELINE.json north_star): per-gene log-likelihood ratios within 1e-4 relative.  Both optimisers
+stop on SciPy's relative-decrease rule with gradients of 1e-3..1e-2 and the ELBO carries ~1e-10 relative
+evaluation noise, so even the reference is only reproducible to ~1e-6..1e-5 in the ELBO, and some fits are
+chaotic at round-off level.  Every fixture therefore carries a second oracle run from a
+start perturbed by 1e-12: fits whose two oracle runs agree are *stable* and must match tightly; the others
+are only required to land on one of the oracle's answers or between them.
+"""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+LL_RTOL = 5e-6      # per-fit ELBO, relative (stable fits)
+LLR_RTOL = 1e-4     # north_star
+LLR_ATOL = 2e-3     # for LLR ~ 0 (constant genes)
+
+
+def _load(name):
+    return np.load(os.path.join(GOLD, name + ".npz"), allow_pickle=True)
+
+
+def _frames(fx):
+    X, Y = fx["X"], fx["Y"]
+    cells = ["c%d" % i for i in range(X.shape[0])]
+    genes = ["g%d" % i for i in range(Y.shape[0])]
+    Xdf = pd.DataFrame(X, index=cells)
+    Ydf = pd.DataFrame(Y, index=genes, columns=cells)
+    sdf = pd.DataFrame(fx["scale"], index=cells) if "scale" in fx.files else None
+    return Xdf, Ydf, sdf
+
+
+def _check_table(df, fx, K, skip=None):
+    got = df.values
+    ref, ref2 = fx["ll"], fx["ll_pert"]
+    assert got.shape == ref.shape
+    n_stable = 0
+    for g in range(ref.shape[0]):
+        for k in range(K):
+            a, b = ref[g, k], ref2[g, k]
+            stable = abs(a - b) <= 1e-6 * abs(a)
+            n_stable += int(stable)
+            if skip is not None and (g, k) in skip:
+                continue
+            tol = max(LL_RTOL * abs(a), 3.0 * abs(a - b))
+            assert abs(got[g, k] - a) <= tol, (g, k, got[g, k], a, b)
+        a, b = ref[g, K], ref2[g, K]
+        if skip is not None and any(gg == g for gg, _ in skip):
+            continue
+        if abs(a - b) <= 1e-5 * abs(a) + 1e-5:
+            assert abs(got[g, K] - a) <= LLR_RTOL * abs(a) + LLR_ATOL, (g, got[g, K], a)
+    assert n_stable >= 0.7 * ref.shape[0] * K
+
+
+@pytest.mark.parametrize("name", ["one_sample_sparse_nb", "one_sample_sparse_poisson", "one_sample_sparse_zinb"])
+def test_one_sample_sparse(name):
+    from gpcounts_b200 import Fit_GPcounts
+    fx = _load(name)
+    Xdf, Ydf, _ = _frames(fx)
+    gp = Fit_GPcounts(Xdf, Ydf, sparse=True, M=int(fx["M"]))
+    df = gp.One_sample_test(str(fx["lik"]))
+    assert list(df.columns) == ["Dynamic_model_log_likelihood", "Constant_model_log_likelihood", "log_likelihood_ratio"]
+    assert list(df.index) == list(Ydf.index)
+    _check_table(df, fx, 2)
+    assert (gp.fit_stats["status"] == 0).all()
+    out = gp.calculate_FDR(df)
+    assert {"p_value", "q_value"} <= set(out.columns)
+
+
+def test_one_sample_vgp_scaled_2d():
+    from gpcounts_b200 import Fit_GPcounts
+    fx = _load("one_sample_vgp_scaled")
+    Xdf, Ydf, sdf = _frames(fx)
+    gp = Fit_GPcounts(Xdf, Ydf, scale=sdf)
+    df = gp.One_sample_test("Negative_binomial")
+    _check_table(df, fx, 2)
+    # the model object of the last gene exposes the attribute paths the reference uses
+    assert np.isfinite(gp.model.likelihood.alpha.numpy())
+    assert np.isfinite(gp.model.kernel.variance.numpy())
+
+
+def test_infer_trajectory_matches_dynamic_column():
+    from gpcounts_b200 import Fit_GPcounts
+    fx = _load("one_sample_sparse_nb")
+    Xdf, Ydf, _ = _frames(fx)
+    gp = Fit_GPcounts(Xdf, Ydf, sparse=True, M=int(fx["M"]))
+    df = gp.Infer_trajectory("Negative_binomial")
+    assert list(df.columns) == ["Dynamic_model_log_likelihood"]
+    ref = fx["ll"][:, 0]
+    stable = np.abs(ref - fx["ll_pert"][:, 0]) <= 1e-6 * np.abs(ref)
+    assert np.all(np.abs(df.values[stable, 0] - ref[stable]) <= LL_RTOL * np.abs(ref[stable]))
+
+
+def test_two_samples():
+    from gpcounts_b200 import Fit_GPcounts
+    fx = _load("two_samples_vgp_nb")
+    Xdf, Ydf, _ = _frames(fx)
+    Xdf.columns = ["times"]
+    gp = Fit_GPcounts(Xdf, Ydf)
+    df = gp.Two_samples_test("Negative_binomial")
+    assert list(df.columns) == ["Shared_log_likelihood", "model_1_log_likelihood", "model_2_log_likelihood",
+                                "log_likelihood_ratio"]
+    _check_table(df, fx, 3)
+
+
+def test_gaussian_gpr():
+    from gpcounts_b200 import Fit_GPcounts
+    fx = _load("one_sample_gpr_gauss")
+    Xdf, Ydf, _ = _frames(fx)
+    gp = Fit_GPcounts(Xdf, Ydf)
+    df = gp.One_sample_test("Gaussian")
+    _check_table(df, fx, 2)
+
+
+def test_branching():
+    from gpcounts_b200 import Fit_GPcounts
+    fx = _load("branching_nb")
+    t, labels, Y = fx["t"], fx["labels"], fx["Y"]
+    cells = ["c%d" % i for i in range(len(t))]
+    gp = Fit_GPcounts(pd.DataFrame(t, index=cells), pd.DataFrame(Y, index=["gene"], columns=cells))
+    res = gp.Infer_branching_location(labels, bins_num=int(fx["bins"]))
+    assert set(res) == {"geneName", "branching_probability", "branching_location", "mean", "variance", "Xnew",
+                        "test_times", "MAP_model", "loglik", "logBayesFactor", "likelihood"}
+    ref, ref2 = fx["loglik"], fx["loglik_pert"]
+    # these small fits stop on the relative-decrease rule while still drifting: the oracle's own two runs differ
+    # by up to 4e-3, which bounds what any second implementation can reproduce
+    tol = np.maximum(3.0 * np.abs(ref - ref2), 2e-5 * np.abs(ref))
+    assert np.all(np.abs(res["loglik"] - ref) <= tol), (res["loglik"], ref, ref2)
+    assert np.allclose(res["branching_probability"], fx["branching_probability"], atol=5e-3)
+    assert abs(res["logBayesFactor"] - float(fx["logBayesFactor"])) < 2e-2
+    assert int(np.argmax(res["branching_probability"])) == int(np.argmax(fx["branching_probability"]))
+
+
+def test_mouseob_golden():
+    """The numbers the reference itself published (GPcounts_spatial.ipynb:1080,1086) for the two genes whose
+    inputs are on disk, plus six genes of data/MouseOB/SE_genes_comparison.csv."""
+    from gpcounts_b200 import Fit_GPcounts
+    fx = _load("mouseob_vgp_scaled")
+    Xdf, Ydf, sdf = _frames(fx)
+    Ydf.index = list(fx["genes"])
+    sdf.columns = list(fx["genes"])
+    gp = Fit_GPcounts(Xdf, Ydf, scale=sdf)
+    df = gp.One_sample_test("Negative_binomial")
+    got = df.values
+    nb = fx["notebook_ll"]
+    # 2010300C02Rik: dynamic and constant ELBO published by the reference
+    assert abs(got[0, 0] - nb[0, 0]) < 5e-5, got[0]
+    # Fit_GPcounts hands alpha to the constant model (:785-787); the notebook API did not -> compare with the oracle
+    # Slc1a3's dynamic fit is chaotic at round-off level in the reference itself: SciPy lands on -1112.0078 or
+    # on -1118.958 depending on a 1e-13 perturbation of the start; accept either optimum
+    _check_table(df, fx, 2, skip={(1, 0), (1, 1)})
+    assert min(abs(got[1, 0] + 1112.00784), abs(got[1, 0] + 1118.9577)) < 2e-3, got[1]
+    paper = fx["paper_llr"]
+    ok = ~np.isnan(paper)
+    stable = np.abs(fx["ll"][:, 2] - fx["ll_pert"][:, 2]) <= 1e-5 * np.abs(fx["ll"][:, 2])
+    sel = ok & stable
+    sel[1] = False      # Slc1a3's dynamic fit is chaotic at round-off level in the reference itself
+    assert np.all(np.abs(got[sel, 2] - paper[sel]) <= 2e-3), (got[:, 2], paper)
