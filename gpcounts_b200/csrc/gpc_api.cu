@@ -47,7 +47,7 @@ static WsLayout make_layout(const gpc_model_t* models, int n_models, int m) {
         const size_t sdim = sparse ? md.M : md.N;
         const size_t mv = model_mv(md);
         const size_t P = GPC_NHYP + mv + mv * (mv + 1) / 2;
-        L.sq = std::max(L.sq, pad8(sdim * sdim));
+        L.sq = std::max(L.sq, std::max(pad8(sdim * sdim), (size_t)4096));   // >= 64 x 64: scratch of the fused evaluator
         L.dinv = std::max(L.dinv, (size_t)((sdim + GPC_BLK - 1) / GPC_BLK) * GPC_BLK * GPC_BLK);
         if (sparse) L.rect = std::max(L.rect, pad8((size_t)md.M * md.N));
         L.vec = std::max(L.vec, pad8((size_t)md.N));
@@ -99,6 +99,11 @@ struct FitArgs {
 };
 
 extern __shared__ __align__(16) unsigned char g_smem[];
+
+// The dense (CtaSmem) and fused (FusedSmem) evaluators overlay the same shared-memory region.
+__host__ __device__ constexpr size_t eval_smem_bytes() {
+    return ((sizeof(CtaSmem) > sizeof(FusedSmem) ? sizeof(CtaSmem) : sizeof(FusedSmem)) + 15) & ~(size_t)15;
+}
 
 __device__ __forceinline__ double softplus_inv_d(double p) { return p + log(-expm1(-p)); }
 
@@ -171,7 +176,7 @@ __device__ bool fit_one(const FitArgs& a, int g, int k, double prev_alpha, const
 
 __global__ void __launch_bounds__(GPC_THREADS) k_fit(FitArgs a) {
     CtaSmem* sm = reinterpret_cast<CtaSmem*>(g_smem);
-    OptSmem* os = reinterpret_cast<OptSmem*>(g_smem + ((sizeof(CtaSmem) + 15) & ~(size_t)15));
+    OptSmem* os = reinterpret_cast<OptSmem*>(g_smem + eval_smem_bytes());
     __shared__ int s_job;
     const SlotWs ws = carve(a.ws + (size_t)blockIdx.x * a.lay.slot, a.lay);
     const int n_jobs = a.chain ? a.D : a.D * a.n_models;
@@ -280,7 +285,7 @@ static const double H_GH_W[GPC_NGH] = {
     1.0901720602002331e-01, 2.4810520887463643e-02, 3.2437733422378567e-03, 2.2833863601635403e-04,
     7.8025564785320632e-06, 1.0860693707692815e-07, 4.3993409922731809e-10, 2.2293936455341505e-13};
 
-static size_t smem_bytes() { return ((sizeof(CtaSmem) + 15) & ~(size_t)15) + sizeof(OptSmem); }
+static size_t smem_bytes() { return eval_smem_bytes() + sizeof(OptSmem); }
 
 static int ensure_init() {
     static bool done[64] = {false};

@@ -15,6 +15,7 @@
 // All scalar logic is executed redundantly by every thread on CTA-uniform values.
 #pragma once
 #include "model.cuh"
+#include "svgp_fused.cuh"
 
 #define GPC_MMAX 10
 #define GPC_EPSMCH 2.220446049250313e-16

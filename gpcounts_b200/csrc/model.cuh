@@ -187,7 +187,7 @@ __device__ void lik_pass(const ModelDev& md, const Hyper& h, int N, const double
 }
 
 // ------------------------------------------------------------------------------------------------ VGP
-__device__ int eval_vgp(const ModelDev& md, const double* y, const double* scale, const double* theta, double* grad,
+__device__ __noinline__ int eval_vgp(const ModelDev& md, const double* y, const double* scale, const double* theta, double* grad,
                         double* f_out, const SlotWs& ws, CtaSmem* sm) {
     const int N = md.N, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const Hyper h = hyper_from_theta(md, theta);
@@ -260,7 +260,7 @@ __device__ int eval_vgp(const ModelDev& md, const double* y, const double* scale
 }
 
 // ------------------------------------------------------------------------------------------------ SVGP
-__device__ int eval_svgp(const ModelDev& md, const double* Z, const double* y, const double* scale,
+__device__ __noinline__ int eval_svgp(const ModelDev& md, const double* Z, const double* y, const double* scale,
                          const double* theta, double* grad, double* f_out, const SlotWs& ws, CtaSmem* sm) {
     const int N = md.N, M = md.M, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const Hyper h = hyper_from_theta(md, theta);
@@ -360,7 +360,7 @@ __device__ int eval_svgp(const ModelDev& md, const double* Z, const double* y, c
 
 // ------------------------------------------------------------------------------------------------ GPR
 // log N(y | 0, K + noise I);  theta = (var, ls, noise, -)
-__device__ int eval_gpr(const ModelDev& md, const double* y, const double* theta, double* grad, double* f_out,
+__device__ __noinline__ int eval_gpr(const ModelDev& md, const double* y, const double* theta, double* grad, double* f_out,
                         const SlotWs& ws, CtaSmem* sm) {
     const int N = md.N, tid = threadIdx.x;
     const Hyper h = hyper_from_theta(md, theta);
@@ -399,8 +399,19 @@ __device__ int eval_gpr(const ModelDev& md, const double* y, const double* theta
     return GPC_ST_OK;
 }
 
+struct FusedSmem;
+__device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z, const double* y, const double* scale,
+                               const double* theta, double* grad, double* f_out, const SlotWs& ws, FusedSmem* fs);
+
+// The on-chip evaluator covers SVGP with M <= 64 inducing points, d <= 2, RBF / Constant kernels.
+__device__ __forceinline__ bool use_fused(const ModelDev& md) {
+    return md.kind == GPC_SVGP && md.M <= 64 && md.d <= 2 && md.kernel != GPC_BRANCH;
+}
+
 __device__ int model_eval(const ModelDev& md, const double* Z, const double* y, const double* scale,
                           const double* theta, double* grad, double* f_out, const SlotWs& ws, CtaSmem* sm) {
+    if (use_fused(md))
+        return eval_svgp_fused(md, Z, y, scale, theta, grad, f_out, ws, reinterpret_cast<FusedSmem*>(sm));
     switch (md.kind) {
         case GPC_VGP: return eval_vgp(md, y, scale, theta, grad, f_out, ws, sm);
         case GPC_SVGP: return eval_svgp(md, Z, y, scale, theta, grad, f_out, ws, sm);

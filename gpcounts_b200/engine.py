@@ -19,7 +19,12 @@ LIK = {"NB": L.GPC_NB, "ZINB": L.GPC_ZINB, "POISSON": L.GPC_POISSON, "GAUSS": L.
 def _dev_f64(a, device):
     if a is None:
         return None
-    t = torch.as_tensor(np.ascontiguousarray(a) if isinstance(a, np.ndarray) else a, dtype=torch.float64)
+    if isinstance(a, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+        if torch.device(device).type == "cuda" and t.numel() >= (1 << 16):
+            t = t.pin_memory()                      # H2D from pinned host memory
+        return t.to(device, non_blocking=True)
+    t = torch.as_tensor(a, dtype=torch.float64)
     return t.to(device).contiguous()
 
 
