@@ -26,11 +26,12 @@ struct FusedSmem {
     double Linv[FZ_MAT];            // Lm^-1 (lower)
     double Lq[FZ_MAT];              // tril(q_sqrt)
     double qmu[64];
-    double gq[64];                  // A g_m accumulator
-    double part[4][64][4];          // per column partial sums (4 parts x 64 columns x 4 values)
-    double col[8][64];              // per column: fmean, fvar, gm, gv, y, scale, 2*gv, valid
+    double gq[64];                  // A g_m accumulator, columns 0..31 of every tile
+    double gq2[64];                 // A g_m accumulator, columns 32..63 (separate so the sums stay deterministic)
+    double col[8][64];              // per column: fmean, fvar, gm, gv, y, scale, 2*gv, -
     double red[64];
     double Zs[64 * 2];              // inducing inputs (d <= 2)
+    double Xs[64 * 2];              // inputs of the current column tile
 };
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
@@ -58,6 +59,53 @@ __device__ __forceinline__ void warp_mma(double (&acc)[8][2], const double* __re
     }
 }
 
+// Four column tiles ctb .. ctb+3 of row block r0 (the balanced half-row-block unit of the M x 64 products).
+template <bool AT, bool BT>
+__device__ __forceinline__ void warp_mma4(double (&acc)[4][2], const double* __restrict__ A, int r0,
+                                          const double* __restrict__ B, int kbeg, int kend, int ctb) {
+    const int lane = threadIdx.x & 31, ar = lane >> 2, ak = lane & 3;
+#pragma unroll 2
+    for (int k0 = kbeg; k0 < kend; k0 += 4) {
+        const double a = AT ? A[(k0 + ak) * FZ_LD + r0 + ar] : A[(r0 + ar) * FZ_LD + k0 + ak];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int ct = ctb + t;
+            const double b = BT ? B[(ct * 8 + ar) * FZ_LD + k0 + ak] : B[(k0 + ak) * FZ_LD + ct * 8 + ar];
+            dmma884(acc[t], a, b);
+        }
+    }
+}
+
+__device__ __forceinline__ void acc4_zero(double (&acc)[4][2]) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+}
+
+__device__ __forceinline__ void acc4_store(const double (&acc)[4][2], double* C, int r0, int ctb) {
+    const int lane = threadIdx.x & 31, ar = lane >> 2, ac = 2 * (lane & 3);
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+        *reinterpret_cast<double2*>(&C[(r0 + ar) * FZ_LD + (ctb + t) * 8 + ac]) = make_double2(acc[t][0], acc[t][1]);
+}
+
+// Rank update with the A fragment scaled per k (column of the tile): acc += (A diag(s)) * B^T, column tiles 0..ct1-1.
+__device__ __forceinline__ void warp_mma_rank(double (&acc)[8][2], const double* __restrict__ A, int r0,
+                                              const double* __restrict__ B, const double* __restrict__ s, int ct1) {
+    const int lane = threadIdx.x & 31, ar = lane >> 2, ak = lane & 3;
+#pragma unroll 2
+    for (int k0 = 0; k0 < 64; k0 += 4) {
+        double a = A[(r0 + ar) * FZ_LD + k0 + ak];
+        if (s) a *= s[k0 + ak];
+#pragma unroll
+        for (int ct = 0; ct < 8; ++ct) {
+            if (ct < ct1) {
+                const double b = B[(ct * 8 + ar) * FZ_LD + k0 + ak];
+                dmma884(acc[ct], a, b);
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ void acc_zero(double (&acc)[8][2]) {
 #pragma unroll
     for (int t = 0; t < 8; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
@@ -72,24 +120,31 @@ __device__ __forceinline__ void acc_store(const double (&acc)[8][2], double* C, 
             *reinterpret_cast<double2*>(&C[(r0 + ar) * FZ_LD + ct * 8 + ac]) = make_double2(acc[ct][0], acc[ct][1]);
 }
 
-// In-place Cholesky of the n x n SPD matrix in smem D (ld FZ_LD, lower part used); false on a bad pivot.
+// Cholesky of the n x n SPD matrix in smem D (ld FZ_LD, lower part used), result in the lower triangle of D.
+// Right-looking with ONE barrier per column: the trailing update of column j reads the *unscaled* column j
+// (D[i][j] D[c][j] / d_jj) while the scaled column is written to its final place by the threads that own it.
 __device__ bool fz_chol(double* D, int n) {
     const int tid = threadIdx.x;
     for (int j = 0; j < n; ++j) {
         __syncthreads();
         const double djj = D[j * FZ_LD + j];
         if (!(djj > 0.0)) return false;
-        const double r = sqrt(djj);
-        __syncthreads();
-        if (tid == j) D[j * FZ_LD + j] = r;
-        if (tid > j && tid < n) D[tid * FZ_LD + j] /= r;
-        __syncthreads();
+        const double inv = 1.0 / djj;
         const int rem = n - j - 1;
+        // trailing update with the unscaled column j (entries (i, c), j < c <= i); columns are scaled at the end
         for (int idx = tid; idx < rem * rem; idx += GPC_THREADS) {
             const int i = j + 1 + idx / rem, c = j + 1 + idx % rem;
-            if (c <= i) D[i * FZ_LD + c] = fma(-D[i * FZ_LD + j], D[c * FZ_LD + j], D[i * FZ_LD + c]);
+            if (c <= i) D[i * FZ_LD + c] = fma(-D[i * FZ_LD + j] * inv, D[c * FZ_LD + j], D[i * FZ_LD + c]);
         }
     }
+    __syncthreads();
+    // scale the columns: L[i][j] = D[i][j] / sqrt(d_jj), L[j][j] = sqrt(d_jj)   (d_jj = final pivot values on the diagonal)
+    for (int idx = tid; idx < n * n; idx += GPC_THREADS) {
+        const int i = idx / n, j = idx % n;
+        if (j < i) D[i * FZ_LD + j] = D[i * FZ_LD + j] / sqrt(D[j * FZ_LD + j]);
+    }
+    __syncthreads();
+    if (tid < n) D[tid * FZ_LD + tid] = sqrt(D[tid * FZ_LD + tid]);
     __syncthreads();
     return true;
 }
@@ -198,8 +253,9 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
 
     // ---- setup: Z, q_mu, Lq, Kuu -> Lm -> Linv ----------------------------------------------------------------
     for (int i = tid; i < 64 * 2; i += GPC_THREADS) fs->Zs[i] = (i < M * dd) ? Z[i] : 0.0;
-    if (tid < 64) { fs->qmu[tid] = tid < M ? q_mu[tid] : 0.0; fs->gq[tid] = 0.0; }
+    if (tid < 64) { fs->qmu[tid] = tid < M ? q_mu[tid] : 0.0; fs->gq[tid] = 0.0; fs->gq2[tid] = 0.0; }
     __syncthreads();
+#pragma unroll 4
     for (int idx = tid; idx < 64 * 64; idx += GPC_THREADS) {
         const int i = idx >> 6, j = idx & 63;
         double lq = (i == j) ? 1.0 : 0.0, kv = 0.0;
@@ -216,58 +272,74 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
     }
     if (!fz_chol(fs->T2, M)) return GPC_ST_CHOL;
     fz_tri_inverse(fs->T2, M, fs->Linv);
-    for (int idx = tid; idx < 64 * 64; idx += GPC_THREADS) {       // keep Lm for the end phase
-        const int i = idx >> 6, j = idx & 63;
-        ws.L[idx] = (i < M && j <= i) ? fs->T2[i * FZ_LD + j] : 0.0;
+    if (need_kg) {
+        for (int idx = tid; idx < 64 * 64; idx += GPC_THREADS) {   // keep Lm for the end phase
+            const int i = idx >> 6, j = idx & 63;
+            ws.L[idx] = (i < M && j <= i) ? fs->T2[i * FZ_LD + j] : 0.0;
+        }
     }
 
     // ---- column tiles -------------------------------------------------------------------------------------------
+    // M x 64 products: warp w owns row block rbA = w for column tiles 0..3 and row block rbB = nrb-1-w for column
+    // tiles 4..7, which balances the triangular k-ranges (cost rb+1 resp. nrb-rb) across warps.
     double accLq[8][2], accLm[8][2];
     acc_zero(accLq);
     acc_zero(accLm);
-    const int rbq = warp, rbm = nrb - 1 - warp;          // row blocks of the two rank updates owned by this warp
-    double sum_ve = 0.0, sum_da = 0.0, sum_dk = 0.0, sum_gv = 0.0, sum_sk = 0.0, sum_skr = 0.0;
-    bool poison_any = false;
-    const int r0 = warp * 8;
     const bool active = warp < nrb;
+    const int rA = warp * 8, rB = (nrb - 1 - warp) * 8;
+    double sum_ve = 0.0, sum_da = 0.0, sum_dk = 0.0, sum_gv = 0.0, sum_sk = 0.0, sum_skr = 0.0;
+    const int ar = lane >> 2, ac = 2 * (lane & 3);
     for (int n0 = 0; n0 < N; n0 += 64) {
         const int nt = min(64, N - n0);
         __syncthreads();
-        // Kuf tile (zero beyond M rows / nt columns); per-column inputs
-        for (int idx = tid; idx < 64 * 64; idx += GPC_THREADS) {
-            const int i = idx >> 6, c = idx & 63;
-            double kv = 0.0;
-            if (i < M && c < nt) {
-                bool cross;
-                const double r2 = kern_r2(kp, fs->Zs + i * dd, md.X + (size_t)(n0 + c) * dd, cross);
-                kv = kern_val(kp, r2, cross);
-            }
-            fs->T0[i * FZ_LD + c] = kv;
-        }
-        if (tid < 64) {
-            const bool v = tid < nt;
-            fs->col[4][tid] = v ? y[n0 + tid] : 0.0;
-            fs->col[5][tid] = (v && scale) ? scale[n0 + tid] : 1.0;
+        if (tid < 64 * dd) fs->Xs[tid] = (tid < nt * dd) ? md.X[(size_t)n0 * dd + tid] : 0.0;
+        if (tid >= 128 && tid < 192) {
+            const int c = tid - 128;
+            const bool v = c < nt;
+            fs->col[4][c] = v ? y[n0 + c] : 0.0;
+            fs->col[5][c] = (v && scale) ? scale[n0 + c] : 1.0;
         }
         __syncthreads();
-        double acc[8][2];
-        // A = Linv * Kuf      (rows r0.., k <= r0 + 7)
-        if (active) {
-            acc_zero(acc);
-            warp_mma<false, false, false>(acc, fs->Linv, r0, fs->T0, 0, r0 + 8, 0, 8);
-            acc_store(acc, fs->T1, r0, 0, 8);
-        }
-        __syncthreads();
-        // B = Lq^T * A        (k >= r0)
-        if (active) {
-            acc_zero(acc);
-            warp_mma<true, false, false>(acc, fs->Lq, r0, fs->T1, r0, Mp, 0, 8);
-            acc_store(acc, fs->T2, r0, 0, 8);
-        }
-        __syncthreads();
-        // per-column statistics: 4 threads per column over the rows
+        // ---- Kuf tile: thread (c = tid & 63) x rows (tid >> 6) + 4 t ------------------------------------------
         {
-            const int c = tid & 63, part = tid >> 6;
+            const int c = tid & 63, ib = tid >> 6;
+            const double* xc = fs->Xs + c * dd;
+            const bool cv = c < nt;
+#pragma unroll 8
+            for (int t = 0; t < 16; ++t) {
+                const int i = ib + 4 * t;
+                double kv = 0.0;
+                if (cv && i < M) {
+                    bool cross;
+                    const double r2 = kern_r2(kp, fs->Zs + i * dd, xc, cross);
+                    kv = kern_val(kp, r2, cross);
+                }
+                fs->T0[i * FZ_LD + c] = kv;
+            }
+        }
+        __syncthreads();
+        double acc[4][2], acc2[4][2];
+        // ---- A = Linv * Kuf (k <= row) -> T1 --------------------------------------------------------------------
+        if (active) {
+            acc4_zero(acc); acc4_zero(acc2);
+            warp_mma4<false, false>(acc, fs->Linv, rA, fs->T0, 0, rA + 8, 0);
+            warp_mma4<false, false>(acc2, fs->Linv, rB, fs->T0, 0, rB + 8, 4);
+            acc4_store(acc, fs->T1, rA, 0);
+            acc4_store(acc2, fs->T1, rB, 4);
+        }
+        __syncthreads();
+        // ---- B = Lq^T * A (k >= row) -> T2 ------------------------------------------------------------------------
+        if (active) {
+            acc4_zero(acc); acc4_zero(acc2);
+            warp_mma4<true, false>(acc, fs->Lq, rA, fs->T1, rA, Mp, 0);
+            warp_mma4<true, false>(acc2, fs->Lq, rB, fs->T1, rB, Mp, 4);
+            acc4_store(acc, fs->T2, rA, 0);
+            acc4_store(acc2, fs->T2, rB, 4);
+        }
+        __syncthreads();
+        // ---- per-column statistics + quadrature: 4 adjacent lanes per column ---------------------------------------
+        {
+            const int c = tid >> 2, part = tid & 3;
             double s1 = 0.0, s2 = 0.0, s3 = 0.0;
             for (int i = part; i < Mp; i += 4) {
                 const double a = fs->T1[i * FZ_LD + c], b = fs->T2[i * FZ_LD + c];
@@ -275,21 +347,10 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
                 s2 = fma(a, a, s2);
                 s3 = fma(b, b, s3);
             }
-            fs->part[part][c][0] = s1; fs->part[part][c][1] = s2; fs->part[part][c][2] = s3;
-        }
-        __syncthreads();
-        if (tid < 64) {
-            double s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-            for (int p = 0; p < 4; ++p) { s1 += fs->part[p][tid][0]; s2 += fs->part[p][tid][1]; s3 += fs->part[p][tid][2]; }
-            fs->col[0][tid] = s1;
-            fs->col[1][tid] = (kdiag - s2) + s3;
-        }
-        __syncthreads();
-        // quadrature: 4 threads per column, 5 nodes each (Poisson: closed form by part 0)
-        {
-            const int c = tid & 63, part = tid >> 6;
-            const double fm = fs->col[0][c], fv = fs->col[1][c], yy = fs->col[4][c];
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+            s3 += __shfl_xor_sync(0xffffffffu, s3, 1); s3 += __shfl_xor_sync(0xffffffffu, s3, 2);
+            const double fm = s1, fv = (kdiag - s2) + s3, yy = fs->col[4][c];
             double ve = 0.0, gm = 0.0, gz = 0.0, da = 0.0, dk = 0.0;
             bool poison = false;
             if (c < nt) {
@@ -305,96 +366,102 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
                     const LikPart o = lik_nodes(lp, fm, sd, yy, log(fs->col[5][c]), part * 5, part * 5 + 5);
                     ve = o.ve; gm = o.gm; gz = o.gz; da = o.da; dk = o.dk; poison = o.poison;
                     const bool has_const = (md.lik == GPC_NB) || (yy != 0.0);
-                    if (part == 1 && has_const) ve += lgamma(lp.k + yy) - lgamma(yy + 1.0) - lp.lgamma_k;
+                    if (part == 1 && has_const) ve += lgamma(lp.k + yy) - lp.lgamma_k;
+                    if (part == 3 && has_const) ve -= lgamma(yy + 1.0);
                     if (part == 2 && has_const) da += -(lp.k * lp.k) * (digamma_pos(lp.k + yy) - lp.digamma_k);
                 }
             }
             if (poison) { gm = NAN; gz = NAN; dk = NAN; }
-            fs->part[part][c][0] = gm; fs->part[part][c][1] = gz;
             sum_ve += ve; sum_da += da; sum_dk += dk;
+            gm += __shfl_xor_sync(0xffffffffu, gm, 1); gm += __shfl_xor_sync(0xffffffffu, gm, 2);
+            gz += __shfl_xor_sync(0xffffffffu, gz, 1); gz += __shfl_xor_sync(0xffffffffu, gz, 2);
+            if (part == 0) {
+                double gv = 0.0;
+                if (c < nt) gv = (md.lik == GPC_POISSON) ? gz : gz / (2.0 * sqrt(fv));
+                else gm = 0.0;
+                fs->col[2][c] = gm;
+                fs->col[6][c] = 2.0 * gv;
+                sum_gv += gv;
+            }
         }
         __syncthreads();
-        if (tid < 64) {
-            double gm = 0.0, gz = 0.0;
-#pragma unroll
-            for (int p = 0; p < 4; ++p) { gm += fs->part[p][tid][0]; gz += fs->part[p][tid][1]; }
-            double gv = 0.0;
-            if (tid < nt) gv = (md.lik == GPC_POISSON) ? gz : gz / (2.0 * sqrt(fs->col[1][tid]));
-            else gm = 0.0;
-            fs->col[2][tid] = gm;
-            fs->col[3][tid] = gv;
-            fs->col[6][tid] = 2.0 * gv;
-            sum_gv += gv;
-        }
-        __syncthreads();
-        // Bbar = B * diag(2 gv) in place;  gq += A gm
-        for (int idx = tid; idx < Mp * 64; idx += GPC_THREADS) {
-            const int i = idx >> 6, c = idx & 63;
-            fs->T2[i * FZ_LD + c] *= fs->col[6][c];
-        }
-        for (int row = warp; row < Mp; row += 8) {
-            double s = fs->T1[row * FZ_LD + lane] * fs->col[2][lane] + fs->T1[row * FZ_LD + lane + 32] * fs->col[2][lane + 32];
-            s = warp_sum(s);
-            if (lane == 0) fs->gq[row] += s;
-        }
-        __syncthreads();
-        // Abar = q_mu gm^T - A diag(2 gv) + Lq * Bbar      (k <= r0 + 7)
+        // ---- Abar = q_mu gm^T - A diag(2 gv) + (Lq * B) diag(2 gv) -> T3;  gq += A gm;  <Abar, A> -------------------
         if (active) {
-            acc_zero(acc);
-            warp_mma<false, false, false>(acc, fs->Lq, r0, fs->T2, 0, r0 + 8, 0, 8);
-            const int ar = lane >> 2, ac = 2 * (lane & 3);
-            const double qm = fs->qmu[r0 + ar];
-            double sab = 0.0;
+            acc4_zero(acc); acc4_zero(acc2);
+            warp_mma4<false, false>(acc, fs->Lq, rA, fs->T2, 0, rA + 8, 0);
+            warp_mma4<false, false>(acc2, fs->Lq, rB, fs->T2, 0, rB + 8, 4);
+            double sab = 0.0, gqa = 0.0, gqb = 0.0;
 #pragma unroll
-            for (int ct = 0; ct < 8; ++ct) {
-                const int c = ct * 8 + ac;
-                const double2 a = *reinterpret_cast<const double2*>(&fs->T1[(r0 + ar) * FZ_LD + c]);
-                const double v0 = acc[ct][0] + qm * fs->col[2][c] - a.x * fs->col[6][c];
-                const double v1 = acc[ct][1] + qm * fs->col[2][c + 1] - a.y * fs->col[6][c + 1];
-                sab = fma(v0, a.x, sab);
-                sab = fma(v1, a.y, sab);
-                *reinterpret_cast<double2*>(&fs->T3[(r0 + ar) * FZ_LD + c]) = make_double2(v0, v1);
+            for (int half = 0; half < 2; ++half) {
+                const int r = (half ? rB : rA) + ar;
+                const double qm = fs->qmu[r];
+                double gql = 0.0;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int c = (half * 4 + t) * 8 + ac;
+                    const double2 a = *reinterpret_cast<const double2*>(&fs->T1[r * FZ_LD + c]);
+                    const double g0 = fs->col[2][c], g1 = fs->col[2][c + 1], w0 = fs->col[6][c], w1 = fs->col[6][c + 1];
+                    const double p0 = half ? acc2[t][0] : acc[t][0], p1 = half ? acc2[t][1] : acc[t][1];
+                    const double v0 = (p0 - a.x) * w0 + qm * g0;
+                    const double v1 = (p1 - a.y) * w1 + qm * g1;
+                    sab = fma(v0, a.x, sab);
+                    sab = fma(v1, a.y, sab);
+                    gql = fma(a.x, g0, gql);
+                    gql = fma(a.y, g1, gql);
+                    *reinterpret_cast<double2*>(&fs->T3[r * FZ_LD + c]) = make_double2(v0, v1);
+                }
+                if (half) gqb = gql; else gqa = gql;
             }
             sum_sk += sab;                                   // <Abar, A> = <S, Kuf>
+            gqa += __shfl_xor_sync(0xffffffffu, gqa, 1); gqa += __shfl_xor_sync(0xffffffffu, gqa, 2);
+            gqb += __shfl_xor_sync(0xffffffffu, gqb, 1); gqb += __shfl_xor_sync(0xffffffffu, gqb, 2);
+            // rows rA.. get their columns 0..31 part here and their columns 32..63 part from the warp whose rB == rA
+            if ((lane & 3) == 0) { fs->gq[rA + ar] += gqa; fs->gq2[rB + ar] += gqb; }
         }
-        // GLq += A * Bbar^T   (row block rbq, column tiles 0..rbq)
-        if (rbq < nrb) warp_mma<false, true, false>(accLq, fs->T1, rbq * 8, fs->T2, 0, 64, 0, rbq + 1);
+        // ---- GLq += (A diag(2 gv)) * B^T   (row block w, column tiles 0..w) --------------------------------------------
+        if (active) warp_mma_rank(accLq, fs->T1, rA, fs->T2, fs->col[6], warp + 1);
         __syncthreads();
         if (need_kg) {
-            // S = Linv^T * Abar   (k >= r0) -> T2
+            // ---- S = Linv^T * Abar (k >= row) -> T2 ----------------------------------------------------------------
             if (active) {
-                acc_zero(acc);
-                warp_mma<true, false, false>(acc, fs->Linv, r0, fs->T3, r0, Mp, 0, 8);
-                acc_store(acc, fs->T2, r0, 0, 8);
+                acc4_zero(acc); acc4_zero(acc2);
+                warp_mma4<true, false>(acc, fs->Linv, rA, fs->T3, rA, Mp, 0);
+                warp_mma4<true, false>(acc2, fs->Linv, rB, fs->T3, rB, Mp, 4);
+                acc4_store(acc, fs->T2, rA, 0);
+                acc4_store(acc2, fs->T2, rB, 4);
             }
             __syncthreads();
-            // GLm += S * A^T      (row block rbm, column tiles 0..rbm)
-            if (rbm >= 0 && rbm < nrb) warp_mma<false, true, false>(accLm, fs->T2, rbm * 8, fs->T1, 0, 64, 0, rbm + 1);
-            // <S o Kuf, R^2>
+            // ---- GLm += S * A^T (row block nrb-1-w, column tiles 0..nrb-1-w);  <S o Kuf, R^2> -------------------------
+            if (active) warp_mma_rank(accLm, fs->T2, rB, fs->T1, nullptr, nrb - warp);
             if (md.kernel != GPC_CONST) {
-                for (int idx = tid; idx < M * 64; idx += GPC_THREADS) {
-                    const int i = idx >> 6, c = idx & 63;
-                    if (c < nt) {
-                        bool cross;
-                        const double r2 = kern_r2(kp, fs->Zs + i * dd, md.X + (size_t)(n0 + c) * dd, cross);
-                        sum_skr = fma(fs->T2[i * FZ_LD + c] * fs->T0[i * FZ_LD + c], r2, sum_skr);
+                const int c = tid & 63, ib = tid >> 6;
+                const double* xc = fs->Xs + c * dd;
+                if (c < nt) {
+#pragma unroll 4
+                    for (int t = 0; t < 16; ++t) {
+                        const int i = ib + 4 * t;
+                        if (i < M) {
+                            bool cross;
+                            const double r2 = kern_r2(kp, fs->Zs + i * dd, xc, cross);
+                            sum_skr = fma(fs->T2[i * FZ_LD + c] * fs->T0[i * FZ_LD + c], r2, sum_skr);
+                        }
                     }
                 }
             }
         }
-        poison_any = poison_any;
     }
     __syncthreads();
     // ---- end phase ------------------------------------------------------------------------------------------------
-    // GLq -> T1 (lower), GLm -> T3 (lower, sign applied later)
     for (int idx = tid; idx < 64 * 64; idx += GPC_THREADS) {
         const int i = idx >> 6, j = idx & 63;
         fs->T1[i * FZ_LD + j] = 0.0;
         fs->T3[i * FZ_LD + j] = 0.0;
     }
     __syncthreads();
-    if (rbq < nrb) acc_store(accLq, fs->T1, rbq * 8, 0, rbq + 1);
-    if (rbm >= 0 && rbm < nrb) acc_store(accLm, fs->T3, rbm * 8, 0, rbm + 1);
+    if (active) {
+        acc_store(accLq, fs->T1, rA, 0, warp + 1);
+        acc_store(accLm, fs->T3, rB, 0, nrb - warp);
+    }
     __syncthreads();
     double* glq = grad + GPC_NHYP + M;
     for (int idx = tid; idx < M * M; idx += GPC_THREADS) {
@@ -404,11 +471,9 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
             glq[tri_index(i, j)] = fs->T1[i * FZ_LD + j] - (i == j ? l - 1.0 / l : l);
         }
     }
-    if (tid < M) grad[GPC_NHYP + tid] = fs->gq[tid] - fs->qmu[tid];
-    // reductions of the per-thread sums
+    if (tid < M) grad[GPC_NHYP + tid] = (fs->gq[tid] + fs->gq2[tid]) - fs->qmu[tid];
     double acc6[6] = {sum_ve, sum_da, sum_dk, sum_gv, sum_sk, sum_skr};
     cta_sum_n<6>(acc6, fs->red);
-    // KL
     double klacc[3] = {0.0, 0.0, 0.0};
     for (int idx = tid; idx < M * M; idx += GPC_THREADS) {
         const int i = idx / M, j = idx % M;
@@ -428,11 +493,11 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
         }
         __syncthreads();
         double acc[8][2];
+        const int r0 = rA;
         // P = Phi(Lm^T * Lmbar) -> T1 (lower):  P[i][j] = sum_{k >= i} Lm[k][i] Lmbar[k][j]
         if (active) {
             acc_zero(acc);
             warp_mma<true, false, false>(acc, fs->T2, r0, fs->T3, r0, Mp, 0, warp + 1);
-            const int ar = lane >> 2, ac = 2 * (lane & 3);
 #pragma unroll
             for (int ct = 0; ct < 8; ++ct) {
                 const int i = r0 + ar, j = ct * 8 + ac;
@@ -466,14 +531,9 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
             kern_grad_acc(kp, fs->T1[i * FZ_LD + j], k0, r2, cross, a2[0], a2[1]);
         }
         cta_sum_n<2>(a2, fs->red);
-        if (md.kernel == GPC_CONST) {
-            gvar = acc6[3] + acc6[4] / h.var + a2[0];
-        } else {
-            // <S, Kuf>/var only holds for kernels proportional to var; BranchKernel cross terms are not, so the
-            // generic path (dense evaluator) handles BRANCH; here RBF: d Kuf / d var = Kuf / var
-            gvar = acc6[3] + acc6[4] / h.var + a2[0];
-            gls = acc6[5] * kp.inv_ls3 + a2[1];
-        }
+        // RBF / Constant: d Kuf / d var = Kuf / var, so <S, dKuf/dvar> = <Abar, A> / var
+        gvar = acc6[3] + acc6[4] / h.var + a2[0];
+        if (md.kernel != GPC_CONST) gls = acc6[5] * kp.inv_ls3 + a2[1];
     }
     store_hyper_grad(md, h, gvar, gls, acc6[1], acc6[2], grad);
     *f_out = acc6[0] - kl;

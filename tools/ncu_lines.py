@@ -53,3 +53,9 @@ for f, n in by_func.most_common(12):
 print()
 for (f, ln), n in by_line.most_common(top):
     print("%6.2f%%  %-28s %s" % (100.0 * n / total, f, ln))
+
+if len(sys.argv) > 4:
+    print("\nby file/line order (>= 0.15%):")
+    for (f, ln), n in sorted(by_line.items(), key=lambda kv: (str(kv[0][1]))):
+        if ln and 100.0 * n / total >= 0.15:
+            print("%6.2f%%  %s" % (100.0 * n / total, ln))
