@@ -30,6 +30,7 @@ struct OptSmem {
     double WN[2 * GPC_MMAX][2 * GPC_MMAX];   // upper-triangular LEL^T factor of the middle matrix
     double wv[2 * GPC_MMAX];
     double dots[GPC_MMAX][6];          // per memory vector: S.d, Y.d, S.r, Y.r, S.g, Y.g
+    double T[GPC_MMAX][GPC_MMAX];      // formt scratch
     int info;
 };
 
@@ -180,87 +181,108 @@ __device__ __forceinline__ int dcsrch_step(DcsrchState& s, double f, double g) {
     return 0;
 }
 
-// Upper Cholesky A = R^T R of the leading n x n block (LINPACK dpofa); returns 0 or the failing pivot.
-__device__ int small_chol_upper(double* A, int lda, int n) {
-    for (int j = 0; j < n; ++j) {
-        double s = 0.0;
-        for (int k = 0; k < j; ++k) {
-            double t = A[k * lda + j];
-            for (int i = 0; i < k; ++i) t -= A[i * lda + k] * A[i * lda + j];
-            t /= A[k * lda + k];
-            A[k * lda + j] = t;
-            s += t * t;
+// The limited-memory matrices are at most 20 x 20; warp 0 works on them cooperatively in shared memory (the rest
+// of the CTA waits at the next barrier).  All routines must be called by every lane of one warp.
+
+// Upper Cholesky A = R^T R of the leading n x n block (LINPACK dpofa semantics: 0 or the failing pivot index).
+__device__ int warp_chol_upper(double* A, int lda, int n) {
+    const int lane = threadIdx.x & 31;
+    for (int k = 0; k < n; ++k) {
+        __syncwarp();
+        const double akk = A[k * lda + k];
+        if (!(akk > 0.0)) return k + 1;
+        const double r = sqrt(akk);
+        __syncwarp();
+        if (lane == 0) A[k * lda + k] = r;
+        for (int j = k + 1 + lane; j < n; j += 32) A[k * lda + j] /= r;
+        __syncwarp();
+        const int rem = n - k - 1;
+        for (int idx = lane; idx < rem * rem; idx += 32) {
+            const int i = k + 1 + idx / rem, j = k + 1 + idx % rem;
+            if (j >= i) A[i * lda + j] -= A[k * lda + i] * A[k * lda + j];
         }
-        s = A[j * lda + j] - s;
-        if (!(s > 0.0)) return j + 1;
-        A[j * lda + j] = sqrt(s);
     }
+    __syncwarp();
     return 0;
 }
 
-// formk for the all-free case, run by thread 0: builds and factors WN (upper triangle). 0 on success.
+// formk for the all-free case: builds and factors WN (upper triangle). 0 on success.
 __device__ int formk_free(OptSmem* os, int col, double theta) {
-    const int L2 = 2 * GPC_MMAX;
+    const int L2 = 2 * GPC_MMAX, lane = threadIdx.x & 31;
     double* WN = &os->WN[0][0];
-    for (int iy = 0; iy < col; ++iy) {
-        for (int jy = 0; jy <= iy; ++jy) {
-            WN[jy * L2 + iy] = os->YY[iy][jy] / theta;                 // Y'Y / theta
-            WN[(col + jy) * L2 + col + iy] = 0.0;                      // theta * S'AA'S = 0 (no active bounds)
+    for (int idx = lane; idx < col * col; idx += 32) {
+        const int iy = idx / col, jy = idx % col;
+        if (jy <= iy) {
+            WN[jy * L2 + iy] = os->YY[iy][jy] / theta + (jy == iy ? os->SY[iy][iy] : 0.0);   // Y'Y / theta + D
+            WN[(col + jy) * L2 + col + iy] = 0.0;                                            // theta * S'AA'S = 0
         }
-        for (int jy = 0; jy < iy; ++jy) WN[jy * L2 + col + iy] = 0.0;  // -L_a' = 0
-        for (int jy = iy; jy < col; ++jy) WN[jy * L2 + col + iy] = os->RZ[iy][jy];   // R_z'
-        WN[iy * L2 + iy] += os->SY[iy][iy];                            // + D
+        WN[jy * L2 + col + iy] = (jy >= iy) ? os->RZ[iy][jy] : 0.0;                           // R_z' (and -L_a' = 0)
     }
-    int info = small_chol_upper(WN, L2, col);
+    __syncwarp();
+    int info = warp_chol_upper(WN, L2, col);
     if (info != 0) return -1;
-    // columns of block (1,2): solve R1^T x = b  (dtrsl job 11)
-    for (int js = col; js < 2 * col; ++js)
+    // columns of block (1,2): solve R1^T x = b  (dtrsl job 11), one lane per column
+    if (lane < col) {
+        const int js = col + lane;
         for (int i = 0; i < col; ++i) {
             double t = WN[i * L2 + js];
             for (int k = 0; k < i; ++k) t -= WN[k * L2 + i] * WN[k * L2 + js];
             WN[i * L2 + js] = t / WN[i * L2 + i];
         }
-    for (int is = col; is < 2 * col; ++is)
-        for (int js = is; js < 2 * col; ++js) {
+    }
+    __syncwarp();
+    for (int idx = lane; idx < col * col; idx += 32) {
+        const int a = idx / col, b = idx % col;
+        if (b >= a) {
             double t = 0.0;
-            for (int k = 0; k < col; ++k) t += WN[k * L2 + is] * WN[k * L2 + js];
-            WN[is * L2 + js] += t;
+            for (int k = 0; k < col; ++k) t += WN[k * L2 + col + a] * WN[k * L2 + col + b];
+            WN[(col + a) * L2 + col + b] += t;
         }
-    info = small_chol_upper(WN + col * L2 + col, L2, col);
+    }
+    __syncwarp();
+    info = warp_chol_upper(WN + col * L2 + col, L2, col);
     if (info != 0) return -2;
     return 0;
 }
 
-// formt: T = theta*SS + L D^-1 L^T must be positive definite (thread 0). 0 on success.
+// formt: T = theta*SS + L D^-1 L^T must be positive definite. 0 on success.
 __device__ int formt_check(OptSmem* os, int col, double theta) {
-    double T[GPC_MMAX * GPC_MMAX];
-    for (int j = 0; j < col; ++j) T[j] = theta * os->SS[0][j];
-    for (int i = 1; i < col; ++i)
-        for (int j = i; j < col; ++j) {
-            const int k1 = min(i, j);
+    const int lane = threadIdx.x & 31;
+    double* T = &os->T[0][0];
+    for (int idx = lane; idx < col * col; idx += 32) {
+        const int i = idx / col, j = idx % col;
+        if (j >= i) {
             double ddum = 0.0;
-            for (int k = 0; k < k1; ++k) ddum += os->SY[i][k] * os->SY[j][k] / os->SY[k][k];
+            for (int k = 0; k < i; ++k) ddum += os->SY[i][k] * os->SY[j][k] / os->SY[k][k];
             T[i * GPC_MMAX + j] = ddum + theta * os->SS[i][j];
         }
-    return small_chol_upper(T, GPC_MMAX, col);
+    }
+    __syncwarp();
+    return warp_chol_upper(T, GPC_MMAX, col);
 }
 
-// subsm middle solve (thread 0): wv <- K^-1 wv through the LEL^T factor.
+// subsm middle solve: wv <- K^-1 wv through the LEL^T factor (column-oriented substitutions).
 __device__ void subsm_solve(OptSmem* os, int col) {
-    const int L2 = 2 * GPC_MMAX, c2 = 2 * col;
+    const int L2 = 2 * GPC_MMAX, c2 = 2 * col, lane = threadIdx.x & 31;
     double* WN = &os->WN[0][0];
     double* wv = os->wv;
     for (int i = 0; i < c2; ++i) {                       // U^T x = b
-        double t = wv[i];
-        for (int k = 0; k < i; ++k) t -= WN[k * L2 + i] * wv[k];
-        wv[i] = t / WN[i * L2 + i];
+        __syncwarp();
+        const double xi = wv[i] / WN[i * L2 + i];
+        __syncwarp();
+        if (lane == 0) wv[i] = xi;
+        for (int k = i + 1 + lane; k < c2; k += 32) wv[k] -= WN[i * L2 + k] * xi;
     }
-    for (int i = 0; i < col; ++i) wv[i] = -wv[i];
+    __syncwarp();
+    if (lane < col) wv[lane] = -wv[lane];
     for (int i = c2 - 1; i >= 0; --i) {                  // U x = b
-        double t = wv[i];
-        for (int k = i + 1; k < c2; ++k) t -= WN[i * L2 + k] * wv[k];
-        wv[i] = t / WN[i * L2 + i];
+        __syncwarp();
+        const double xi = wv[i] / WN[i * L2 + i];
+        __syncwarp();
+        if (lane == 0) wv[i] = xi;
+        for (int k = lane; k < i; k += 32) wv[k] -= WN[k * L2 + i] * xi;
     }
+    __syncwarp();
 }
 
 struct OptResult {
@@ -344,17 +366,18 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
                 ws.d[i] = zi - ws.x[i];
             }
         } else {
-            if (tid == 0) {
+            if (warp == 0) {
                 int info = 0;
                 if (updated) info = formk_free(os, col, theta);
                 if (info == 0) {
-                    for (int j = 0; j < col; ++j) {
-                        os->wv[j] = -os->dots[j][5];                 // Y_j . r, r = -g
-                        os->wv[col + j] = -theta * os->dots[j][4];   // theta * S_j . r
+                    if (lane < col) {
+                        os->wv[lane] = -os->dots[lane][5];                 // Y_j . r, r = -g
+                        os->wv[col + lane] = -theta * os->dots[lane][4];   // theta * S_j . r
                     }
+                    __syncwarp();
                     subsm_solve(os, col);
                 }
-                os->info = info;
+                if (lane == 0) os->info = info;
             }
             __syncthreads();
             const int info = os->info;
@@ -492,17 +515,23 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
                 for (int q = 0; q < 6; ++q) os->dots[j][q] = a[q];
         }
         __syncthreads();
-        if (!skip && tid == 0) {
+        if (!skip && warp == 0) {
             const int c = col - 1;
-            for (int j = 0; j < col; ++j) {
+            if (lane < col) {
+                const int j = lane;
                 os->SS[j][c] = os->SS[c][j] = os->dots[j][0];
                 os->YY[j][c] = os->YY[c][j] = os->dots[j][3];
                 os->SY[c][j] = os->dots[j][1];        // s_new . y_j
                 os->RZ[j][c] = os->dots[j][2];        // s_j . y_new (diagonal included)
             }
-            os->SS[c][c] = (stp == 1.0) ? dtd : stp * stp * dtd;
-            os->SY[c][c] = dr;
-            os->info = formt_check(os, col, theta);
+            __syncwarp();
+            if (lane == 0) {
+                os->SS[c][c] = (stp == 1.0) ? dtd : stp * stp * dtd;
+                os->SY[c][c] = dr;
+            }
+            __syncwarp();
+            const int info = formt_check(os, col, theta);
+            if (lane == 0) os->info = info;
         }
         __syncthreads();
         if (!skip) {

@@ -130,11 +130,13 @@ __device__ bool fz_chol(double* D, int n) {
         const double djj = D[j * FZ_LD + j];
         if (!(djj > 0.0)) return false;
         const double inv = 1.0 / djj;
-        const int rem = n - j - 1;
-        // trailing update with the unscaled column j (entries (i, c), j < c <= i); columns are scaled at the end
-        for (int idx = tid; idx < rem * rem; idx += GPC_THREADS) {
-            const int i = j + 1 + idx / rem, c = j + 1 + idx % rem;
-            if (c <= i) D[i * FZ_LD + c] = fma(-D[i * FZ_LD + j] * inv, D[c * FZ_LD + j], D[i * FZ_LD + c]);
+        // trailing update with the unscaled column j (entries (i, c), j < c <= i); columns are scaled at the end.
+        // thread (row = tid >> 2, q = tid & 3) walks its row in steps of 4
+        const int i = tid >> 2;
+        if (i > j && i < n) {
+            const double lij = -D[i * FZ_LD + j] * inv;
+            for (int c = j + 1 + (tid & 3); c <= i; c += 4)
+                D[i * FZ_LD + c] = fma(lij, D[c * FZ_LD + j], D[i * FZ_LD + c]);
         }
     }
     __syncthreads();
@@ -305,14 +307,22 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
             const int c = tid & 63, ib = tid >> 6;
             const double* xc = fs->Xs + c * dd;
             const bool cv = c < nt;
-#pragma unroll 8
+            const double x0 = xc[0], x1 = dd > 1 ? xc[1] : 0.0;
+            const double ce = -0.5 * kp.inv_ls2;
+            const bool is_const = md.kernel == GPC_CONST;
+#pragma unroll
             for (int t = 0; t < 16; ++t) {
                 const int i = ib + 4 * t;
                 double kv = 0.0;
                 if (cv && i < M) {
-                    bool cross;
-                    const double r2 = kern_r2(kp, fs->Zs + i * dd, xc, cross);
-                    kv = kern_val(kp, r2, cross);
+                    if (is_const) {
+                        kv = kp.var;
+                    } else {
+                        const double u = fs->Zs[i * dd] - x0;
+                        double r2 = u * u;
+                        if (dd > 1) { const double v = fs->Zs[i * dd + 1] - x1; r2 = fma(v, v, r2); }
+                        kv = kp.var * exp(ce * r2);
+                    }
                 }
                 fs->T0[i * FZ_LD + c] = kv;
             }
@@ -437,12 +447,14 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
                 const int c = tid & 63, ib = tid >> 6;
                 const double* xc = fs->Xs + c * dd;
                 if (c < nt) {
-#pragma unroll 4
+                    const double x0 = xc[0], x1 = dd > 1 ? xc[1] : 0.0;
+#pragma unroll
                     for (int t = 0; t < 16; ++t) {
                         const int i = ib + 4 * t;
                         if (i < M) {
-                            bool cross;
-                            const double r2 = kern_r2(kp, fs->Zs + i * dd, xc, cross);
+                            const double u = fs->Zs[i * dd] - x0;
+                            double r2 = u * u;
+                            if (dd > 1) { const double v = fs->Zs[i * dd + 1] - x1; r2 = fma(v, v, r2); }
                             sum_skr = fma(fs->T2[i * FZ_LD + c] * fs->T0[i * FZ_LD + c], r2, sum_skr);
                         }
                     }
