@@ -50,10 +50,10 @@ static WsLayout make_layout(const gpc_model_t* models, int n_models, int m) {
         L.sq = std::max(L.sq, std::max(pad8(sdim * sdim), (size_t)4096));   // >= 64 x 64: scratch of the fused evaluator
         L.dinv = std::max(L.dinv, (size_t)((sdim + GPC_BLK - 1) / GPC_BLK) * GPC_BLK * GPC_BLK);
         if (sparse) L.rect = std::max(L.rect, pad8((size_t)md.M * md.N));
-        L.vec = std::max(L.vec, pad8((size_t)md.N));
+        L.vec = std::max(L.vec, pad8((size_t)std::max(md.N, md.M)));
         L.pvec = std::max(L.pvec, pad8(P));
     }
-    L.slot = 7 * L.sq + L.dinv + 4 * L.rect + 4 * L.vec + (size_t)(6 + 2 * m) * L.pvec;
+    L.slot = 7 * L.sq + 2 * L.dinv + 4 * L.rect + 4 * L.vec + (size_t)(6 + 2 * m) * L.pvec;
     return L;
 }
 
@@ -62,8 +62,8 @@ __device__ __forceinline__ SlotWs carve(double* base, const WsLayout& L) {
     double* p = base;
     w.K0 = p; p += L.sq; w.L = p; p += L.sq; w.Lq = p; p += L.sq;
     w.G1 = p; p += L.sq; w.G2 = p; p += L.sq; w.G3 = p; p += L.sq;
-    p += L.sq;   // spare square buffer (SGPR)
-    w.dinv = p; p += L.dinv;
+    w.G4 = p; p += L.sq;
+    w.dinv = p; p += L.dinv; w.dinv2 = p; p += L.dinv;
     w.Kuf = p; p += L.rect; w.A = p; p += L.rect; w.B = p; p += L.rect; w.S = p; p += L.rect;
     w.v0 = p; p += L.vec; w.v1 = p; p += L.vec; w.v2 = p; p += L.vec; w.v3 = p; p += L.vec;
     w.x = p; p += L.pvec; w.g = p; p += L.pvec; w.d = p; p += L.pvec;
@@ -307,7 +307,6 @@ static int ensure_init() {
 
 static int check_model(const gpc_model_t& md) {
     if (md.kind < GPC_VGP || md.kind > GPC_SGPR) return set_err(GPC_E_ARG, "bad model kind%s");
-    if (md.kind == GPC_SGPR) return set_err(GPC_E_UNSUPPORTED, "SGPR is not implemented yet%s");
     if (md.kernel < GPC_RBF || md.kernel > GPC_BRANCH) return set_err(GPC_E_ARG, "bad kernel%s");
     if (md.lik < GPC_NB || md.lik > GPC_GAUSS) return set_err(GPC_E_ARG, "bad likelihood%s");
     if ((md.kind == GPC_GPR || md.kind == GPC_SGPR) != (md.lik == GPC_GAUSS))

@@ -24,7 +24,7 @@ struct ModelDev {
 
 // Per-slot workspace carved from the caller's buffer.
 struct SlotWs {
-    double *K0, *L, *dinv, *Lq, *G1, *G2, *G3;   // Mv x Mv (dinv: nblk x 64 x 64)
+    double *K0, *L, *dinv, *Lq, *G1, *G2, *G3, *G4, *dinv2;   // square buffers (dinv: nblk x 64 x 64)
     double *Kuf, *A, *B, *S;                      // M x N   (sparse models)
     double *v0, *v1, *v2, *v3;                    // N
     double *x, *g, *d, *xold, *gold, *z, *WS, *WY;   // optimiser vectors (P) and memory (m x P)
@@ -399,6 +399,114 @@ __device__ __noinline__ int eval_gpr(const ModelDev& md, const double* y, const 
     return GPC_ST_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ SGPR
+// Titsias collapsed bound (gpflow.models.SGPR.elbo; reference call site GPcounts_Module.py:661-663):
+//   V = L^-1 Kuf,  B = V V^T / s2 + I = LB LB^T,  c = LB^-1 V y / s2
+//   F = -N/2 log 2pi - sum log LB_ii - N/2 log s2 - y'y/(2 s2) + c'c/2 - sum(kdiag)/(2 s2) + tr(V V^T)/(2 s2)
+// theta = (var, ls, noise s2, -); reverse pass through both Cholesky factors.
+__device__ __noinline__ int eval_sgpr(const ModelDev& md, const double* Z, const double* y, const double* theta,
+                                      double* grad, double* f_out, const SlotWs& ws, CtaSmem* sm) {
+    const int N = md.N, M = md.M, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const Hyper h = hyper_from_theta(md, theta);
+    KernParams kp;
+    kern_setup(kp, md, h.var, h.ls);
+    const double s2 = h.alpha, is2 = 1.0 / s2;
+    const double shift = md.jitter + (md.kernel == GPC_BRANCH ? GPC_BRANCH_NOISE : 0.0);
+    const double kdiag = h.var + (md.kernel == GPC_BRANCH ? GPC_BRANCH_NOISE : 0.0);
+    double* V = ws.A; double* Vb = ws.B; double* Bm = ws.Lq; double* VVt = ws.G4;
+    double* cvec = ws.v0; double* wvec = ws.v1; double* uvec = ws.v2;
+    build_gram_square(kp, M, Z, shift, ws.K0, ws.L);
+    for (int idx = tid; idx < M * N; idx += GPC_THREADS) {
+        const int i = idx / N, n = idx % N;
+        bool cross;
+        const double r2 = kern_r2(kp, Z + (size_t)i * kp.d, md.X + (size_t)n * kp.d, cross);
+        const double k = kern_val(kp, r2, cross);
+        ws.Kuf[idx] = k;
+        V[idx] = k;
+    }
+    __syncthreads();
+    if (!cta_potrf(M, ws.L, M, ws.dinv, sm)) return GPC_ST_CHOL;
+    cta_trsm_left(M, N, ws.L, M, ws.dinv, V, N, sm);
+    // VVt = V V^T / s2 (full), B = VVt + I
+    cta_gemm<false, true>(M, M, N, is2, V, N, V, N, 0.0, VVt, M, 0, sm);
+    double acc[2] = {0.0, 0.0};
+    for (int idx = tid; idx < M * M; idx += GPC_THREADS) {
+        const int i = idx / M, j = idx % M;
+        const double v = VVt[idx];
+        Bm[idx] = (i == j) ? v + 1.0 : v;
+        if (i == j) acc[0] += v;                       // tr(V V^T) / s2
+    }
+    for (int n = tid; n < N; n += GPC_THREADS) acc[1] = fma(y[n], y[n], acc[1]);
+    cta_sum_n<2>(acc, sm->red);
+    const double trvv = acc[0], yy = acc[1];
+    if (!cta_potrf(M, Bm, M, ws.dinv2, sm)) return GPC_ST_CHOL;
+    // u = V y;  a = u / s2;  c = LB^-1 a;  w = LB^-T c
+    for (int row = warp; row < M; row += GPC_THREADS / 32) {
+        double s = 0.0;
+        for (int n = lane; n < N; n += 32) s = fma(V[(size_t)row * N + n], y[n], s);
+        s = warp_sum(s);
+        if (lane == 0) { uvec[row] = s; cvec[row] = s * is2; }
+    }
+    __syncthreads();
+    cta_trsm_left(M, 1, Bm, M, ws.dinv2, cvec, 1, sm);
+    double a3[3] = {0.0, 0.0, 0.0};
+    for (int i = tid; i < M; i += GPC_THREADS) {
+        wvec[i] = cvec[i];
+        a3[0] = fma(cvec[i], cvec[i], a3[0]);
+        a3[1] += log(Bm[(size_t)i * M + i]);
+    }
+    cta_sum_n<3>(a3, sm->red);
+    const double cc = a3[0], logdetLB = a3[1];
+    cta_trsm_left_t(M, 1, Bm, M, ws.dinv2, wvec, 1, sm);
+    // LB-bar = -tril(w c^T) - diag(1 / LB_ii)  -> G2;  reverse pass of chol(B)
+    for (int idx = tid; idx < M * M; idx += GPC_THREADS) {
+        const int i = idx / M, j = idx % M;
+        if (j <= i) ws.G2[idx] = -wvec[i] * cvec[j] - (i == j ? 1.0 / Bm[idx] : 0.0);
+    }
+    __syncthreads();
+    cta_chol_backward(M, Bm, M, ws.dinv2, ws.G2, M, ws.G3, M, sm);
+    // W = Bbar + Bbar^T -> G1;  <Bbar, VVt>;  w . a
+    double a2[2] = {0.0, 0.0};
+    for (int idx = tid; idx < M * M; idx += GPC_THREADS) {
+        const int i = idx / M, j = idx % M;
+        ws.G1[idx] = ws.G2[idx] + ws.G2[(size_t)j * M + i];
+        a2[0] = fma(ws.G2[idx], VVt[idx], a2[0]);
+    }
+    for (int i = tid; i < M; i += GPC_THREADS) a2[1] = fma(wvec[i], uvec[i] * is2, a2[1]);
+    cta_sum_n<2>(a2, sm->red);
+    // Vbar = (W V + w y^T + V) / s2
+    cta_gemm<false, false>(M, N, M, is2, ws.G1, M, V, N, 0.0, Vb, N, 0, sm);
+    for (int idx = tid; idx < M * N; idx += GPC_THREADS) {
+        const int i = idx / N, n = idx % N;
+        Vb[idx] += (wvec[i] * y[n] + V[idx]) * is2;
+    }
+    __syncthreads();
+    cta_trsm_left_t(M, N, ws.L, M, ws.dinv, Vb, N, sm);                         // S = L^-T Vbar = Kuf-bar
+    cta_gemm<false, true>(M, M, N, -1.0, Vb, N, V, N, 0.0, ws.G2, M, F_C_LOWER, sm);   // L-bar = -tril(S V^T)
+    double ak[2] = {0.0, 0.0};
+    for (int idx = tid; idx < M * N; idx += GPC_THREADS) {
+        const int i = idx / N, n = idx % N;
+        bool cross;
+        const double r2 = kern_r2(kp, Z + (size_t)i * kp.d, md.X + (size_t)n * kp.d, cross);
+        kern_grad_acc(kp, Vb[idx], ws.Kuf[idx], r2, cross, ak[0], ak[1]);
+    }
+    cta_sum_n<2>(ak, sm->red);
+    cta_chol_backward(M, ws.L, M, ws.dinv, ws.G2, M, ws.G3, M, sm);
+    double guu_var, guu_ls;
+    gram_square_grad(kp, M, Z, ws.K0, ws.G2, guu_var, guu_ls, sm);
+    const double gvar = guu_var + ak[0] - 0.5 * N * is2;
+    const double gls = guu_ls + ak[1];
+    // d/d s2: explicit terms + through B (= -<Bbar, VVt> / s2) + through a (= -w.a / s2) + tr term
+    const double gs2 = -0.5 * N * is2 + 0.5 * yy * is2 * is2 + 0.5 * N * kdiag * is2 * is2 - 0.5 * trvv * is2
+                       - a2[0] * is2 - a2[1] * is2;
+    store_hyper_grad(md, h, gvar, gls, gs2, 0.0, grad);
+    *f_out = -0.5 * N * 1.8378770664093453 - logdetLB - 0.5 * N * log(s2) - 0.5 * yy * is2 + 0.5 * cc
+             - 0.5 * N * kdiag * is2 + 0.5 * trvv;
+    __syncthreads();
+    return GPC_ST_OK;
+}
+
 struct FusedSmem;
 __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z, const double* y, const double* scale,
                                const double* theta, double* grad, double* f_out, const SlotWs& ws, FusedSmem* fs);
@@ -416,6 +524,7 @@ __device__ int model_eval(const ModelDev& md, const double* Z, const double* y, 
         case GPC_VGP: return eval_vgp(md, y, scale, theta, grad, f_out, ws, sm);
         case GPC_SVGP: return eval_svgp(md, Z, y, scale, theta, grad, f_out, ws, sm);
         case GPC_GPR: return eval_gpr(md, y, theta, grad, f_out, ws, sm);
+        case GPC_SGPR: return eval_sgpr(md, Z, y, theta, grad, f_out, ws, sm);
         default: return GPC_ST_CHOL;
     }
 }

@@ -104,6 +104,13 @@ def case_gauss():
     save("one_sample_gpr_gauss", X=X, Y=Y, lik="Gaussian", **res)
 
 
+def case_gauss_sparse():
+    D, N, M = 4, 80, 8
+    X, Y = synth_counts(D, N, seed=35)
+    res = run_tests(dict(X=X, Y=Y, sparse=True, M=M, inducing_variance=1.0), "one_sample_test", ("Gaussian",), D)
+    save("one_sample_sgpr_gauss", X=X, Y=Y, M=M, lik="Gaussian", **res)
+
+
 def case_branching():
     N, bins = 40, 5
     rng = np.random.default_rng(7)
@@ -155,6 +162,7 @@ CASES = {
     "vgp_scaled": case_one_sample_vgp_scaled,
     "two_samples": case_two_samples,
     "gauss": case_gauss,
+    "gauss_sparse": case_gauss_sparse,
     "branching": case_branching,
     "mouseob": case_mouseob,
 }

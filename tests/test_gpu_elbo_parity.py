@@ -91,6 +91,11 @@ def test_gpr(kernel):
     _compare("GPR", kernel, "GAUSS", N=70)
 
 
+@pytest.mark.parametrize("kernel,M", [("RBF", 12), ("CONST", 12), ("RBF", 70)])
+def test_sgpr(kernel, M):
+    _compare("SGPR", kernel, "GAUSS", N=150, M=M)
+
+
 def test_not_positive_definite_is_reported():
     from gpcounts_b200 import engine
     from oracle import gp_math as gm

@@ -119,6 +119,15 @@ def test_gaussian_gpr():
     _check_table(df, fx, 2)
 
 
+def test_gaussian_sgpr():
+    from gpcounts_b200 import Fit_GPcounts
+    fx = _load("one_sample_sgpr_gauss")
+    Xdf, Ydf, _ = _frames(fx)
+    gp = Fit_GPcounts(Xdf, Ydf, sparse=True, M=int(fx["M"]))
+    df = gp.One_sample_test("Gaussian")
+    _check_table(df, fx, 2)
+
+
 def test_branching():
     from gpcounts_b200 import Fit_GPcounts
     fx = _load("branching_nb")
