@@ -12,7 +12,9 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#ifndef GPC_THREADS
 #define GPC_THREADS 256
+#endif
 #define GPC_BLK 64                 // block size of the blocked factorisations (= GEMM tile edge)
 #define GPC_BK 16                 // GEMM k-panel
 #define GPC_LDS 66                // padded leading dimension of the staged GEMM panels

@@ -7,9 +7,12 @@
 // Genes never communicate: sharding over GPUs is a partition of the job list.
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "../../include/gpcounts_b200.h"
-#include "lbfgsb.cuh"
+#define GPC_VARIANT t256
+#include "kernels.cuh"
+
 
 static thread_local char g_err[512] = "";
 static double* g_trace = nullptr;
@@ -19,234 +22,6 @@ static long long g_launches = 0;
 static int set_err(int code, const char* fmt, const char* a = "") {
     snprintf(g_err, sizeof(g_err), fmt, a);
     return code;
-}
-
-// ---------------------------------------------------------------------------------------------- layout
-struct WsLayout {
-    size_t sq;          // doubles per square buffer
-    size_t dinv;        // doubles of diagonal-block inverses
-    size_t rect;        // doubles per M x N buffer
-    size_t vec;         // doubles per N vector
-    size_t pvec;        // doubles per parameter vector (padded)
-    int m;              // L-BFGS memory
-    size_t slot;        // doubles per slot
-};
-
-static inline size_t pad8(size_t x) { return (x + 7) & ~(size_t)7; }
-
-static int model_mv(const gpc_model_t& md) {
-    return md.kind == GPC_VGP ? md.N : (md.kind == GPC_SVGP ? md.M : 0);
-}
-
-static WsLayout make_layout(const gpc_model_t* models, int n_models, int m) {
-    WsLayout L{};
-    L.m = m;
-    for (int k = 0; k < n_models; ++k) {
-        const gpc_model_t& md = models[k];
-        const bool sparse = md.kind == GPC_SVGP || md.kind == GPC_SGPR;
-        const size_t sdim = sparse ? md.M : md.N;
-        const size_t mv = model_mv(md);
-        const size_t P = GPC_NHYP + mv + mv * (mv + 1) / 2;
-        L.sq = std::max(L.sq, std::max(pad8(sdim * sdim), (size_t)4096));   // >= 64 x 64: scratch of the fused evaluator
-        L.dinv = std::max(L.dinv, (size_t)((sdim + GPC_BLK - 1) / GPC_BLK) * GPC_BLK * GPC_BLK);
-        if (sparse) L.rect = std::max(L.rect, pad8((size_t)md.M * md.N));
-        L.vec = std::max(L.vec, pad8((size_t)std::max(md.N, md.M)));
-        L.pvec = std::max(L.pvec, pad8(P));
-    }
-    L.slot = 7 * L.sq + 2 * L.dinv + 4 * L.rect + 4 * L.vec + (size_t)(6 + 2 * m) * L.pvec;
-    return L;
-}
-
-__device__ __forceinline__ SlotWs carve(double* base, const WsLayout& L) {
-    SlotWs w;
-    double* p = base;
-    w.K0 = p; p += L.sq; w.L = p; p += L.sq; w.Lq = p; p += L.sq;
-    w.G1 = p; p += L.sq; w.G2 = p; p += L.sq; w.G3 = p; p += L.sq;
-    w.G4 = p; p += L.sq;
-    w.dinv = p; p += L.dinv; w.dinv2 = p; p += L.dinv;
-    w.Kuf = p; p += L.rect; w.A = p; p += L.rect; w.B = p; p += L.rect; w.S = p; p += L.rect;
-    w.v0 = p; p += L.vec; w.v1 = p; p += L.vec; w.v2 = p; p += L.vec; w.v3 = p; p += L.vec;
-    w.x = p; p += L.pvec; w.g = p; p += L.pvec; w.d = p; p += L.pvec;
-    w.xold = p; p += L.pvec; w.gold = p; p += L.pvec; w.z = p; p += L.pvec;
-    w.WS = p; p += (size_t)L.m * L.pvec; w.WY = p;
-    return w;
-}
-
-__host__ __device__ static inline ModelDev to_dev(const gpc_model_t& md) {
-    ModelDev d;
-    d.kind = md.kind; d.kernel = md.kernel; d.lik = md.lik; d.N = md.N; d.M = md.M; d.d = md.d;
-    d.n_off = md.n_off; d.train_mask = md.train_mask; d.n_zsets = md.n_zsets; d.handoff_alpha = md.handoff_alpha;
-    d.xp = md.xp; d.jitter = md.jitter; d.X = md.X; d.Z = md.Z; d.Zgene = md.Zgene; d.restart = md.restart;
-    d.Mv = md.kind == GPC_VGP ? md.N : (md.kind == GPC_SVGP ? md.M : 0);
-    d.P = GPC_NHYP + d.Mv + d.Mv * (d.Mv + 1) / 2;
-    return d;
-}
-
-// ---------------------------------------------------------------------------------------------- kernels
-#define GPC_MAX_MODELS_CONST 64
-struct FitArgs {
-    const ModelDev* models;   // device array
-    int n_models, chain, D;
-    gpc_opt_t opt;
-    const double *Y, *scale, *hyp0;
-    long long ldy, ld_theta;
-    double *stats, *theta_out;
-    double* ws;
-    int* queue;
-    WsLayout lay;
-    double* trace;            // debug: evaluation trace of (trace_gene, trace_model), 8 doubles per evaluation
-    int trace_cap, trace_gene, trace_model;
-};
-
-extern __shared__ __align__(16) unsigned char g_smem[];
-
-// The dense (CtaSmem) and fused (FusedSmem) evaluators overlay the same shared-memory region.
-__host__ __device__ constexpr size_t eval_smem_bytes() {
-    return ((sizeof(CtaSmem) > sizeof(FusedSmem) ? sizeof(CtaSmem) : sizeof(FusedSmem)) + 15) & ~(size_t)15;
-}
-
-__device__ __forceinline__ double softplus_inv_d(double p) { return p + log(-expm1(-p)); }
-
-// Fit one (gene, model); returns true when the fit succeeded. prev_alpha < 0: no hand-off.
-__device__ bool fit_one(const FitArgs& a, int g, int k, double prev_alpha, const SlotWs& ws, CtaSmem* sm, OptSmem* os,
-                        double& alpha_out) {
-    const ModelDev md = a.models[k];
-    const int tid = threadIdx.x;
-    const double* y = a.Y + (size_t)g * a.ldy + md.n_off;
-    const double* scale = a.scale ? a.scale + (size_t)g * a.ldy + md.n_off : nullptr;
-    const double* h0 = a.hyp0 + ((size_t)g * a.n_models + k) * 4;
-    double* st = a.stats + ((size_t)g * a.n_models + k) * GPC_NSTAT;
-    const int max_restart = md.restart ? GPC_MAX_RESTART : 0;
-    int nfev_total = 0;
-    OptResult r;
-    int attempt = 0;
-    bool ok = false;
-    for (;; ++attempt) {
-        double var, ls, alpha, km;
-        if (attempt == 0) {
-            var = h0[0]; ls = h0[1]; alpha = h0[2]; km = h0[3];
-            if (md.handoff_alpha && prev_alpha > 0.0) alpha = prev_alpha;
-        } else {
-            const double* t = md.restart + (size_t)(attempt - 1) * 4;
-            ls = t[0]; var = t[1]; alpha = t[2]; km = t[3];
-        }
-        if (md.kernel == GPC_CONST) ls = 1.0;
-        // theta0: hyper-parameters through softplus^-1, q_mu = 0, q_sqrt = I
-        for (int i = tid; i < md.P; i += GPC_THREADS) ws.x[i] = 0.0;
-        __syncthreads();
-        if (tid == 0) {
-            ws.x[0] = softplus_inv_d(var);
-            ws.x[1] = softplus_inv_d(ls);
-            ws.x[2] = softplus_inv_d(md.lik == GPC_GAUSS ? alpha - GPC_GAUSS_VAR_LOWER : alpha);
-            ws.x[3] = softplus_inv_d(km);
-        }
-        for (int i = tid; i < md.Mv; i += GPC_THREADS) ws.x[GPC_NHYP + md.Mv + tri_index(i, i)] = 1.0;
-        __syncthreads();
-        const double* Z = md.Z ? md.Z + (size_t)(md.n_zsets > 1 ? attempt : 0) * md.M * md.d : nullptr;
-        if (attempt == 0 && md.Zgene) Z = md.Zgene + (size_t)g * md.M * md.d;
-        OptTrace tr{nullptr, 0, 0};
-        if (a.trace && g == a.trace_gene && k == a.trace_model && attempt == 0) { tr.buf = a.trace; tr.cap = a.trace_cap; }
-        r = lbfgsb_minimize(md, Z, y, scale, a.opt, ws, sm, os, &tr);
-        nfev_total += r.nfev;
-        ok = (r.task == TASK_PGTOL || r.task == TASK_FTOL);
-        if (ok || attempt >= max_restart) break;
-    }
-    __syncthreads();
-    const Hyper h = hyper_from_theta(md, ws.x);
-    alpha_out = h.alpha;
-    if (tid == 0) {
-        st[GPC_S_LL] = ok ? -r.f : NAN;
-        st[GPC_S_STATUS] = ok ? GPC_ST_OK : (r.task == TASK_CHOL ? GPC_ST_CHOL : GPC_ST_OPT);
-        st[GPC_S_NIT] = r.nit;
-        st[GPC_S_NFEV] = r.nfev;
-        st[GPC_S_RESTARTS] = attempt;
-        st[GPC_S_VAR] = h.var; st[GPC_S_LS] = h.ls; st[GPC_S_ALPHA] = h.alpha; st[GPC_S_KM] = h.km;
-        st[GPC_S_NFEV_TOTAL] = nfev_total;
-        st[GPC_S_GNORM] = r.gnorm;
-        st[GPC_S_TASK] = r.task;
-        for (int q = 12; q < GPC_NSTAT; ++q) st[q] = 0.0;
-    }
-    if (a.theta_out) {
-        double* out = a.theta_out + ((size_t)g * a.n_models + k) * a.ld_theta;
-        for (int i = tid; i < md.P; i += GPC_THREADS) out[i] = ws.x[i];
-    }
-    __syncthreads();
-    return ok;
-}
-
-__global__ void __launch_bounds__(GPC_THREADS) k_fit(FitArgs a) {
-    CtaSmem* sm = reinterpret_cast<CtaSmem*>(g_smem);
-    OptSmem* os = reinterpret_cast<OptSmem*>(g_smem + eval_smem_bytes());
-    __shared__ int s_job;
-    const SlotWs ws = carve(a.ws + (size_t)blockIdx.x * a.lay.slot, a.lay);
-    const int n_jobs = a.chain ? a.D : a.D * a.n_models;
-    while (true) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_job = atomicAdd(a.queue, 1);
-        __syncthreads();
-        const int job = s_job;
-        if (job >= n_jobs) break;
-        if (a.chain) {
-            double prev_alpha = -1.0;
-            bool alive = true;
-            for (int k = 0; k < a.n_models; ++k) {
-                if (!alive) {
-                    if (threadIdx.x == 0) {
-                        double* st = a.stats + ((size_t)job * a.n_models + k) * GPC_NSTAT;
-                        for (int q = 0; q < GPC_NSTAT; ++q) st[q] = 0.0;
-                        st[GPC_S_LL] = NAN;
-                        st[GPC_S_STATUS] = GPC_ST_SKIPPED;
-                    }
-                    continue;
-                }
-                double alpha_out;
-                alive = fit_one(a, job, k, prev_alpha, ws, sm, os, alpha_out);
-                prev_alpha = alpha_out;
-            }
-        } else {
-            double alpha_out;
-            fit_one(a, job / a.n_models, job % a.n_models, -1.0, ws, sm, os, alpha_out);
-        }
-    }
-}
-
-struct EvalArgs {
-    ModelDev md;
-    int D, zset;
-    const double *Y, *scale, *theta;
-    long long ldy;
-    double *elbo, *grad;
-    int* status;
-    double* ws;
-    int* queue;
-    WsLayout lay;
-};
-
-__global__ void __launch_bounds__(GPC_THREADS) k_elbo_grad(EvalArgs a) {
-    CtaSmem* sm = reinterpret_cast<CtaSmem*>(g_smem);
-    __shared__ int s_job;
-    const SlotWs ws = carve(a.ws + (size_t)blockIdx.x * a.lay.slot, a.lay);
-    const ModelDev md = a.md;
-    while (true) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_job = atomicAdd(a.queue, 1);
-        __syncthreads();
-        const int g = s_job;
-        if (g >= a.D) break;
-        const double* y = a.Y + (size_t)g * a.ldy + md.n_off;
-        const double* scale = a.scale ? a.scale + (size_t)g * a.ldy + md.n_off : nullptr;
-        const double* Z = md.Z ? md.Z + (size_t)a.zset * md.M * md.d : nullptr;
-        if (md.Zgene) Z = md.Zgene + (size_t)g * md.M * md.d;
-        double* grad = a.grad + (size_t)g * md.P;
-        double f;
-        const int st = model_eval(md, Z, y, scale, a.theta + (size_t)g * md.P, grad, &f, ws, sm);
-        if (st != GPC_ST_OK)
-            for (int i = threadIdx.x; i < md.P; i += GPC_THREADS) grad[i] = NAN;
-        if (threadIdx.x == 0) {
-            a.elbo[g] = st == GPC_ST_OK ? f : NAN;
-            a.status[g] = st;
-        }
-    }
 }
 
 __global__ void __launch_bounds__(GPC_THREADS) k_dbg_linalg(int op, int n, int nrhs, double* A, double* B,
@@ -287,6 +62,20 @@ static const double H_GH_W[GPC_NGH] = {
 
 static size_t smem_bytes() { return eval_smem_bytes() + sizeof(OptSmem); }
 
+// Kernel instantiations.  Only the 256-thread one is built: a 512-thread, fused-evaluator-only instantiation
+// (kernels.cuh supports it through GPC_THREADS / GPC_FUSED_ONLY) was measured slower on B200 (494 vs 452 us per
+// C5 evaluation) because its 128-register cap spills the evaluator's accumulators - see DESIGN.md.
+static VariantOps g_ops[1];
+
+static bool host_use_fused(const gpc_model_t& md) {
+    return md.kind == GPC_SVGP && md.M <= 64 && md.d <= 2 && md.kernel != GPC_BRANCH;
+}
+
+static int pick_variant(const gpc_model_t* models, int n_models) {
+    (void)models; (void)n_models; (void)host_use_fused;
+    return 0;
+}
+
 static int ensure_init() {
     static bool done[64] = {false};
     int dev = 0;
@@ -295,12 +84,11 @@ static int ensure_init() {
     double z[GPC_NGH], w[GPC_NGH];
     const double s2 = 1.4142135623730951, sp = 1.7724538509055159;
     for (int i = 0; i < GPC_NGH; ++i) { z[i] = H_GH_X[i] * s2; w[i] = H_GH_W[i] / sp; }
-    if (cudaMemcpyToSymbol(c_gh_z, z, sizeof(z)) != cudaSuccess || cudaMemcpyToSymbol(c_gh_w, w, sizeof(w)) != cudaSuccess)
-        return set_err(GPC_E_LAUNCH, "constant upload failed: %s", cudaGetErrorString(cudaGetLastError()));
-    const int sb = (int)smem_bytes();
-    cudaFuncSetAttribute(k_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-    cudaFuncSetAttribute(k_elbo_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-    cudaFuncSetAttribute(k_dbg_linalg, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+    g_ops[0] = gpc_variant_ops_t256();
+    for (int v = 0; v < 1; ++v)
+        if (g_ops[v].upload_constants(z, w) != 0)
+            return set_err(GPC_E_LAUNCH, "constant upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFuncSetAttribute(k_dbg_linalg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes());
     if (dev < 64) done[dev] = true;
     return 0;
 }
@@ -331,11 +119,9 @@ int64_t gpc_param_count(const gpc_model_t* model) {
 }
 
 int32_t gpc_default_slots(const gpc_model_t* models, int32_t n_models) {
-    (void)models; (void)n_models;
     int dev = 0, sms = 148, per_sm = 1;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (ensure_init() == 0)
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fit, GPC_THREADS, smem_bytes());
+    if (ensure_init() == 0) per_sm = g_ops[models ? pick_variant(models, n_models) : 0].occupancy();
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 2) per_sm = 2;
     return sms * per_sm;
@@ -369,9 +155,8 @@ int gpc_elbo_grad(const gpc_model_t* model, int32_t D, const double* Y, const do
     a.lay = L;
     cudaMemsetAsync(a.queue, 0, 256, s);
     const int grid = n_slots < D ? n_slots : D;
-    k_elbo_grad<<<grid, GPC_THREADS, smem_bytes(), s>>>(a);
+    cudaError_t e = g_ops[pick_variant(model, 1)].launch_eval(&a, grid, s);
     ++g_launches;
-    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_err(GPC_E_LAUNCH, "gpc_elbo_grad launch: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -414,9 +199,8 @@ int gpc_fit(const gpc_model_t* models, int32_t n_models, int32_t chain, const gp
     cudaMemsetAsync(a.queue, 0, 256, s);
     const int n_jobs = chain ? D : D * n_models;
     const int grid = n_slots < n_jobs ? n_slots : n_jobs;
-    k_fit<<<grid, GPC_THREADS, smem_bytes(), s>>>(a);
+    cudaError_t e = g_ops[pick_variant(models, n_models)].launch_fit(&a, grid, s);
     ++g_launches;
-    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_err(GPC_E_LAUNCH, "gpc_fit launch: %s", cudaGetErrorString(e));
     return 0;
 }

@@ -518,6 +518,9 @@ __device__ __forceinline__ bool use_fused(const ModelDev& md) {
 
 __device__ int model_eval(const ModelDev& md, const double* Z, const double* y, const double* scale,
                           const double* theta, double* grad, double* f_out, const SlotWs& ws, CtaSmem* sm) {
+#ifdef GPC_FUSED_ONLY
+    return eval_svgp_fused(md, Z, y, scale, theta, grad, f_out, ws, reinterpret_cast<FusedSmem*>(sm));
+#else
     if (use_fused(md))
         return eval_svgp_fused(md, Z, y, scale, theta, grad, f_out, ws, reinterpret_cast<FusedSmem*>(sm));
     switch (md.kind) {
@@ -527,4 +530,5 @@ __device__ int model_eval(const ModelDev& md, const double* Z, const double* y, 
         case GPC_SGPR: return eval_sgpr(md, Z, y, theta, grad, f_out, ws, sm);
         default: return GPC_ST_CHOL;
     }
+#endif
 }

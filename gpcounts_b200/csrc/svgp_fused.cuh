@@ -17,6 +17,12 @@
 
 #define FZ_LD 68                    // leading dimension of every smem matrix (== 4 mod 16: conflict-free DMMA fragments)
 #define FZ_MAT (64 * FZ_LD)         // doubles per 64 x 64 smem matrix
+#define FZ_NW (GPC_THREADS / 32)    // warps per CTA: 8 or 16
+#define FZ_WPR (FZ_NW / 8)          // warps sharing one pair of row blocks: 1 or 2
+#define FZ_TPH (4 / FZ_WPR)         // column tiles per warp in each half of an M x 64 product: 4 or 2
+#define FZ_RT (8 / FZ_WPR)          // rank-update tiles per warp and matrix: 8 or 4
+#define FZ_LPC (GPC_THREADS / 64)   // lanes per data column in the statistics / quadrature phase: 4 or 8
+#define FZ_RPT (64 / FZ_LPC)        // rows per thread when a thread owns a column: 16 or 8
 
 struct FusedSmem {
     double T0[FZ_MAT];              // Kuf tile            (end phase: Kuu0 / scratch)
@@ -26,8 +32,7 @@ struct FusedSmem {
     double Linv[FZ_MAT];            // Lm^-1 (lower)
     double Lq[FZ_MAT];              // tril(q_sqrt)
     double qmu[64];
-    double gq[64];                  // A g_m accumulator, columns 0..31 of every tile
-    double gq2[64];                 // A g_m accumulator, columns 32..63 (separate so the sums stay deterministic)
+    double gq[2 * FZ_WPR][64];      // A g_m accumulators, one per column group of a tile (deterministic sums)
     double col[8][64];              // per column: fmean, fvar, gm, gv, y, scale, 2*gv, -
     double red[64];
     double Zs[64 * 2];              // inducing inputs (d <= 2)
@@ -59,16 +64,16 @@ __device__ __forceinline__ void warp_mma(double (&acc)[8][2], const double* __re
     }
 }
 
-// Four column tiles ctb .. ctb+3 of row block r0 (the balanced half-row-block unit of the M x 64 products).
-template <bool AT, bool BT>
-__device__ __forceinline__ void warp_mma4(double (&acc)[4][2], const double* __restrict__ A, int r0,
+// NT column tiles ctb .. ctb+NT-1 of row block r0 (the balanced half-row-block unit of the M x 64 products).
+template <bool AT, bool BT, int NT>
+__device__ __forceinline__ void warp_mmaT(double (&acc)[NT][2], const double* __restrict__ A, int r0,
                                           const double* __restrict__ B, int kbeg, int kend, int ctb) {
     const int lane = threadIdx.x & 31, ar = lane >> 2, ak = lane & 3;
 #pragma unroll 2
     for (int k0 = kbeg; k0 < kend; k0 += 4) {
         const double a = AT ? A[(k0 + ak) * FZ_LD + r0 + ar] : A[(r0 + ar) * FZ_LD + k0 + ak];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
+        for (int t = 0; t < NT; ++t) {
             const int ct = ctb + t;
             const double b = BT ? B[(ct * 8 + ar) * FZ_LD + k0 + ak] : B[(k0 + ak) * FZ_LD + ct * 8 + ar];
             dmma884(acc[t], a, b);
@@ -76,31 +81,36 @@ __device__ __forceinline__ void warp_mma4(double (&acc)[4][2], const double* __r
     }
 }
 
-__device__ __forceinline__ void acc4_zero(double (&acc)[4][2]) {
+template <int NT>
+__device__ __forceinline__ void accT_zero(double (&acc)[NT][2]) {
 #pragma unroll
-    for (int t = 0; t < 4; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+    for (int t = 0; t < NT; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
 }
 
-__device__ __forceinline__ void acc4_store(const double (&acc)[4][2], double* C, int r0, int ctb) {
+template <int NT>
+__device__ __forceinline__ void accT_store(const double (&acc)[NT][2], double* C, int r0, int ctb) {
     const int lane = threadIdx.x & 31, ar = lane >> 2, ac = 2 * (lane & 3);
 #pragma unroll
-    for (int t = 0; t < 4; ++t)
+    for (int t = 0; t < NT; ++t)
         *reinterpret_cast<double2*>(&C[(r0 + ar) * FZ_LD + (ctb + t) * 8 + ac]) = make_double2(acc[t][0], acc[t][1]);
 }
 
-// Rank update with the A fragment scaled per k (column of the tile): acc += (A diag(s)) * B^T, column tiles 0..ct1-1.
-__device__ __forceinline__ void warp_mma_rank(double (&acc)[8][2], const double* __restrict__ A, int r0,
-                                              const double* __restrict__ B, const double* __restrict__ s, int ct1) {
+// Rank update over the 64 columns of a tile with the A fragment scaled per column:
+//   acc[t] += (A diag(s)) * B^T for column tiles ct = ct0 + t * FZ_WPR < ct_end  (row block r0 of the M x M result).
+__device__ __forceinline__ void warp_mma_rank(double (&acc)[FZ_RT][2], const double* __restrict__ A, int r0,
+                                              const double* __restrict__ B, const double* __restrict__ s, int ct0,
+                                              int ct_end) {
     const int lane = threadIdx.x & 31, ar = lane >> 2, ak = lane & 3;
 #pragma unroll 2
     for (int k0 = 0; k0 < 64; k0 += 4) {
         double a = A[(r0 + ar) * FZ_LD + k0 + ak];
         if (s) a *= s[k0 + ak];
 #pragma unroll
-        for (int ct = 0; ct < 8; ++ct) {
-            if (ct < ct1) {
+        for (int t = 0; t < FZ_RT; ++t) {
+            const int ct = ct0 + t * FZ_WPR;
+            if (ct < ct_end) {
                 const double b = B[(ct * 8 + ar) * FZ_LD + k0 + ak];
-                dmma884(acc[ct], a, b);
+                dmma884(acc[t], a, b);
             }
         }
     }
@@ -176,7 +186,7 @@ __device__ void fz_tri_inverse(const double* L, int n, double* X) {
 #pragma unroll
         for (int t = 0; t < 16; ++t)
             if (q + 4 * t == i) xk[t] = xi;
-        if (q == 0) X[i * FZ_LD + c] = xi;
+        if (q == 0 && c < 64) X[i * FZ_LD + c] = xi;
     }
     __syncthreads();
 }
@@ -186,10 +196,10 @@ __device__ void fz_tri_inverse(const double* L, int n, double* X) {
 struct LikPart { double ve, gm, gz, da, dk; bool poison; };
 
 __device__ __forceinline__ LikPart lik_nodes(const LikParams& lp, double fm, double sd, double y, double logs, int i0,
-                                             int i1) {
+                                             int istep) {
     LikPart o{0.0, 0.0, 0.0, 0.0, 0.0, false};
     const double alpha = lp.alpha, k = lp.k, ia = k, ia2 = k * k, km = lp.km;
-    for (int i = i0; i < i1; ++i) {
+    for (int i = i0; i < GPC_NGH; i += istep) {
         const double z = c_gh_z[i], w = c_gh_w[i];
         if (lp.lik == GPC_NB) {
             const double logm = fm + sd * z + logs;
@@ -255,7 +265,11 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
 
     // ---- setup: Z, q_mu, Lq, Kuu -> Lm -> Linv ----------------------------------------------------------------
     for (int i = tid; i < 64 * 2; i += GPC_THREADS) fs->Zs[i] = (i < M * dd) ? Z[i] : 0.0;
-    if (tid < 64) { fs->qmu[tid] = tid < M ? q_mu[tid] : 0.0; fs->gq[tid] = 0.0; fs->gq2[tid] = 0.0; }
+    if (tid < 64) {
+        fs->qmu[tid] = tid < M ? q_mu[tid] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 2 * FZ_WPR; ++q) fs->gq[q][tid] = 0.0;
+    }
     __syncthreads();
 #pragma unroll 4
     for (int idx = tid; idx < 64 * 64; idx += GPC_THREADS) {
@@ -282,13 +296,15 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
     }
 
     // ---- column tiles -------------------------------------------------------------------------------------------
-    // M x 64 products: warp w owns row block rbA = w for column tiles 0..3 and row block rbB = nrb-1-w for column
-    // tiles 4..7, which balances the triangular k-ranges (cost rb+1 resp. nrb-rb) across warps.
-    double accLq[8][2], accLm[8][2];
-    acc_zero(accLq);
-    acc_zero(accLm);
-    const bool active = warp < nrb;
-    const int rA = warp * 8, rB = (nrb - 1 - warp) * 8;
+    // M x 64 products: the FZ_WPR warps of pair p own row block p for column tiles 0..3 and row block nrb-1-p for
+    // column tiles 4..7 (FZ_TPH tiles each), which balances the triangular k-ranges (cost rb+1 resp. nrb-rb).
+    double accLq[FZ_RT][2], accLm[FZ_RT][2];
+    accT_zero<FZ_RT>(accLq);
+    accT_zero<FZ_RT>(accLm);
+    const int pr = warp / FZ_WPR, hw = warp % FZ_WPR;
+    const bool active = pr < nrb;
+    const int rA = pr * 8, rB = (nrb - 1 - pr) * 8;
+    const int ctA = hw * FZ_TPH, ctB = 4 + hw * FZ_TPH;
     double sum_ve = 0.0, sum_da = 0.0, sum_dk = 0.0, sum_gv = 0.0, sum_sk = 0.0, sum_skr = 0.0;
     const int ar = lane >> 2, ac = 2 * (lane & 3);
     for (int n0 = 0; n0 < N; n0 += 64) {
@@ -302,7 +318,7 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
             fs->col[5][c] = (v && scale) ? scale[n0 + c] : 1.0;
         }
         __syncthreads();
-        // ---- Kuf tile: thread (c = tid & 63) x rows (tid >> 6) + 4 t ------------------------------------------
+        // ---- Kuf tile: thread owns column c = tid & 63, rows (tid >> 6) + FZ_LPC t ---------------------------------
         {
             const int c = tid & 63, ib = tid >> 6;
             const double* xc = fs->Xs + c * dd;
@@ -311,8 +327,8 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
             const double ce = -0.5 * kp.inv_ls2;
             const bool is_const = md.kernel == GPC_CONST;
 #pragma unroll
-            for (int t = 0; t < 16; ++t) {
-                const int i = ib + 4 * t;
+            for (int t = 0; t < FZ_RPT; ++t) {
+                const int i = ib + FZ_LPC * t;
                 double kv = 0.0;
                 if (cv && i < M) {
                     if (is_const) {
@@ -328,38 +344,41 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
             }
         }
         __syncthreads();
-        double acc[4][2], acc2[4][2];
+        double acc[FZ_TPH][2], acc2[FZ_TPH][2];
         // ---- A = Linv * Kuf (k <= row) -> T1 --------------------------------------------------------------------
         if (active) {
-            acc4_zero(acc); acc4_zero(acc2);
-            warp_mma4<false, false>(acc, fs->Linv, rA, fs->T0, 0, rA + 8, 0);
-            warp_mma4<false, false>(acc2, fs->Linv, rB, fs->T0, 0, rB + 8, 4);
-            acc4_store(acc, fs->T1, rA, 0);
-            acc4_store(acc2, fs->T1, rB, 4);
+            accT_zero<FZ_TPH>(acc); accT_zero<FZ_TPH>(acc2);
+            warp_mmaT<false, false, FZ_TPH>(acc, fs->Linv, rA, fs->T0, 0, rA + 8, ctA);
+            warp_mmaT<false, false, FZ_TPH>(acc2, fs->Linv, rB, fs->T0, 0, rB + 8, ctB);
+            accT_store<FZ_TPH>(acc, fs->T1, rA, ctA);
+            accT_store<FZ_TPH>(acc2, fs->T1, rB, ctB);
         }
         __syncthreads();
         // ---- B = Lq^T * A (k >= row) -> T2 ------------------------------------------------------------------------
         if (active) {
-            acc4_zero(acc); acc4_zero(acc2);
-            warp_mma4<true, false>(acc, fs->Lq, rA, fs->T1, rA, Mp, 0);
-            warp_mma4<true, false>(acc2, fs->Lq, rB, fs->T1, rB, Mp, 4);
-            acc4_store(acc, fs->T2, rA, 0);
-            acc4_store(acc2, fs->T2, rB, 4);
+            accT_zero<FZ_TPH>(acc); accT_zero<FZ_TPH>(acc2);
+            warp_mmaT<true, false, FZ_TPH>(acc, fs->Lq, rA, fs->T1, rA, Mp, ctA);
+            warp_mmaT<true, false, FZ_TPH>(acc2, fs->Lq, rB, fs->T1, rB, Mp, ctB);
+            accT_store<FZ_TPH>(acc, fs->T2, rA, ctA);
+            accT_store<FZ_TPH>(acc2, fs->T2, rB, ctB);
         }
         __syncthreads();
-        // ---- per-column statistics + quadrature: 4 adjacent lanes per column ---------------------------------------
+        // ---- per-column statistics + quadrature: FZ_LPC adjacent lanes per column ---------------------------------
         {
-            const int c = tid >> 2, part = tid & 3;
+            const int c = tid / FZ_LPC, part = tid % FZ_LPC;
             double s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            for (int i = part; i < Mp; i += 4) {
+            for (int i = part; i < Mp; i += FZ_LPC) {
                 const double a = fs->T1[i * FZ_LD + c], b = fs->T2[i * FZ_LD + c];
                 s1 = fma(a, fs->qmu[i], s1);
                 s2 = fma(a, a, s2);
                 s3 = fma(b, b, s3);
             }
-            s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-            s3 += __shfl_xor_sync(0xffffffffu, s3, 1); s3 += __shfl_xor_sync(0xffffffffu, s3, 2);
+#pragma unroll
+            for (int o = 1; o < FZ_LPC; o <<= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+            }
             const double fm = s1, fv = (kdiag - s2) + s3, yy = fs->col[4][c];
             double ve = 0.0, gm = 0.0, gz = 0.0, da = 0.0, dk = 0.0;
             bool poison = false;
@@ -373,18 +392,22 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
                     }
                 } else {
                     const double sd = sqrt(fv);
-                    const LikPart o = lik_nodes(lp, fm, sd, yy, log(fs->col[5][c]), part * 5, part * 5 + 5);
+                    const LikPart o = lik_nodes(lp, fm, sd, yy, log(fs->col[5][c]), part, FZ_LPC);
                     ve = o.ve; gm = o.gm; gz = o.gz; da = o.da; dk = o.dk; poison = o.poison;
+                    // the node-independent lgamma / digamma terms go to the lanes with the fewest nodes
                     const bool has_const = (md.lik == GPC_NB) || (yy != 0.0);
-                    if (part == 1 && has_const) ve += lgamma(lp.k + yy) - lp.lgamma_k;
-                    if (part == 3 && has_const) ve -= lgamma(yy + 1.0);
-                    if (part == 2 && has_const) da += -(lp.k * lp.k) * (digamma_pos(lp.k + yy) - lp.digamma_k);
+                    if (part == FZ_LPC - 3 && has_const) ve += lgamma(lp.k + yy) - lp.lgamma_k;
+                    if (part == FZ_LPC - 1 && has_const) ve -= lgamma(yy + 1.0);
+                    if (part == FZ_LPC - 2 && has_const) da += -(lp.k * lp.k) * (digamma_pos(lp.k + yy) - lp.digamma_k);
                 }
             }
             if (poison) { gm = NAN; gz = NAN; dk = NAN; }
             sum_ve += ve; sum_da += da; sum_dk += dk;
-            gm += __shfl_xor_sync(0xffffffffu, gm, 1); gm += __shfl_xor_sync(0xffffffffu, gm, 2);
-            gz += __shfl_xor_sync(0xffffffffu, gz, 1); gz += __shfl_xor_sync(0xffffffffu, gz, 2);
+#pragma unroll
+            for (int o = 1; o < FZ_LPC; o <<= 1) {
+                gm += __shfl_xor_sync(0xffffffffu, gm, o);
+                gz += __shfl_xor_sync(0xffffffffu, gz, o);
+            }
             if (part == 0) {
                 double gv = 0.0;
                 if (c < nt) gv = (md.lik == GPC_POISSON) ? gz : gz / (2.0 * sqrt(fv));
@@ -397,9 +420,9 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
         __syncthreads();
         // ---- Abar = q_mu gm^T - A diag(2 gv) + (Lq * B) diag(2 gv) -> T3;  gq += A gm;  <Abar, A> -------------------
         if (active) {
-            acc4_zero(acc); acc4_zero(acc2);
-            warp_mma4<false, false>(acc, fs->Lq, rA, fs->T2, 0, rA + 8, 0);
-            warp_mma4<false, false>(acc2, fs->Lq, rB, fs->T2, 0, rB + 8, 4);
+            accT_zero<FZ_TPH>(acc); accT_zero<FZ_TPH>(acc2);
+            warp_mmaT<false, false, FZ_TPH>(acc, fs->Lq, rA, fs->T2, 0, rA + 8, ctA);
+            warp_mmaT<false, false, FZ_TPH>(acc2, fs->Lq, rB, fs->T2, 0, rB + 8, ctB);
             double sab = 0.0, gqa = 0.0, gqb = 0.0;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -407,8 +430,8 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
                 const double qm = fs->qmu[r];
                 double gql = 0.0;
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int c = (half * 4 + t) * 8 + ac;
+                for (int t = 0; t < FZ_TPH; ++t) {
+                    const int c = ((half ? ctB : ctA) + t) * 8 + ac;
                     const double2 a = *reinterpret_cast<const double2*>(&fs->T1[r * FZ_LD + c]);
                     const double g0 = fs->col[2][c], g1 = fs->col[2][c + 1], w0 = fs->col[6][c], w1 = fs->col[6][c + 1];
                     const double p0 = half ? acc2[t][0] : acc[t][0], p1 = half ? acc2[t][1] : acc[t][1];
@@ -425,32 +448,32 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
             sum_sk += sab;                                   // <Abar, A> = <S, Kuf>
             gqa += __shfl_xor_sync(0xffffffffu, gqa, 1); gqa += __shfl_xor_sync(0xffffffffu, gqa, 2);
             gqb += __shfl_xor_sync(0xffffffffu, gqb, 1); gqb += __shfl_xor_sync(0xffffffffu, gqb, 2);
-            // rows rA.. get their columns 0..31 part here and their columns 32..63 part from the warp whose rB == rA
-            if ((lane & 3) == 0) { fs->gq[rA + ar] += gqa; fs->gq2[rB + ar] += gqb; }
+            // each (row, column group) partial sum has exactly one writer
+            if ((lane & 3) == 0) { fs->gq[hw][rA + ar] += gqa; fs->gq[FZ_WPR + hw][rB + ar] += gqb; }
         }
-        // ---- GLq += (A diag(2 gv)) * B^T   (row block w, column tiles 0..w) --------------------------------------------
-        if (active) warp_mma_rank(accLq, fs->T1, rA, fs->T2, fs->col[6], warp + 1);
+        // ---- GLq += (A diag(2 gv)) * B^T   (row block p, column tiles hw, hw + FZ_WPR, ... <= p) ------------------------
+        if (active) warp_mma_rank(accLq, fs->T1, rA, fs->T2, fs->col[6], hw, pr + 1);
         __syncthreads();
         if (need_kg) {
             // ---- S = Linv^T * Abar (k >= row) -> T2 ----------------------------------------------------------------
             if (active) {
-                acc4_zero(acc); acc4_zero(acc2);
-                warp_mma4<true, false>(acc, fs->Linv, rA, fs->T3, rA, Mp, 0);
-                warp_mma4<true, false>(acc2, fs->Linv, rB, fs->T3, rB, Mp, 4);
-                acc4_store(acc, fs->T2, rA, 0);
-                acc4_store(acc2, fs->T2, rB, 4);
+                accT_zero<FZ_TPH>(acc); accT_zero<FZ_TPH>(acc2);
+                warp_mmaT<true, false, FZ_TPH>(acc, fs->Linv, rA, fs->T3, rA, Mp, ctA);
+                warp_mmaT<true, false, FZ_TPH>(acc2, fs->Linv, rB, fs->T3, rB, Mp, ctB);
+                accT_store<FZ_TPH>(acc, fs->T2, rA, ctA);
+                accT_store<FZ_TPH>(acc2, fs->T2, rB, ctB);
             }
             __syncthreads();
-            // ---- GLm += S * A^T (row block nrb-1-w, column tiles 0..nrb-1-w);  <S o Kuf, R^2> -------------------------
-            if (active) warp_mma_rank(accLm, fs->T2, rB, fs->T1, nullptr, nrb - warp);
+            // ---- GLm += S * A^T (row block nrb-1-p, its column tiles);  <S o Kuf, R^2> ---------------------------------
+            if (active) warp_mma_rank(accLm, fs->T2, rB, fs->T1, nullptr, hw, nrb - pr);
             if (md.kernel != GPC_CONST) {
                 const int c = tid & 63, ib = tid >> 6;
                 const double* xc = fs->Xs + c * dd;
                 if (c < nt) {
                     const double x0 = xc[0], x1 = dd > 1 ? xc[1] : 0.0;
 #pragma unroll
-                    for (int t = 0; t < 16; ++t) {
-                        const int i = ib + 4 * t;
+                    for (int t = 0; t < FZ_RPT; ++t) {
+                        const int i = ib + FZ_LPC * t;
                         if (i < M) {
                             const double u = fs->Zs[i * dd] - x0;
                             double r2 = u * u;
@@ -471,8 +494,15 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
     }
     __syncthreads();
     if (active) {
-        acc_store(accLq, fs->T1, rA, 0, warp + 1);
-        acc_store(accLm, fs->T3, rB, 0, nrb - warp);
+        const int ar2 = lane >> 2, ac2 = 2 * (lane & 3);
+#pragma unroll
+        for (int t = 0; t < FZ_RT; ++t) {
+            const int ct = hw + t * FZ_WPR;
+            if (ct <= pr)
+                *reinterpret_cast<double2*>(&fs->T1[(rA + ar2) * FZ_LD + ct * 8 + ac2]) = make_double2(accLq[t][0], accLq[t][1]);
+            if (ct < nrb - pr)
+                *reinterpret_cast<double2*>(&fs->T3[(rB + ar2) * FZ_LD + ct * 8 + ac2]) = make_double2(accLm[t][0], accLm[t][1]);
+        }
     }
     __syncthreads();
     double* glq = grad + GPC_NHYP + M;
@@ -483,7 +513,12 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
             glq[tri_index(i, j)] = fs->T1[i * FZ_LD + j] - (i == j ? l - 1.0 / l : l);
         }
     }
-    if (tid < M) grad[GPC_NHYP + tid] = (fs->gq[tid] + fs->gq2[tid]) - fs->qmu[tid];
+    if (tid < M) {
+        double gsum = 0.0;
+#pragma unroll
+        for (int q = 0; q < 2 * FZ_WPR; ++q) gsum += fs->gq[q][tid];
+        grad[GPC_NHYP + tid] = gsum - fs->qmu[tid];
+    }
     double acc6[6] = {sum_ve, sum_da, sum_dk, sum_gv, sum_sk, sum_skr};
     cta_sum_n<6>(acc6, fs->red);
     double klacc[3] = {0.0, 0.0, 0.0};
@@ -505,7 +540,8 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
         }
         __syncthreads();
         double acc[8][2];
-        const int r0 = rA;
+        const int r0 = warp * 8;
+        const bool active = warp < nrb;
         // P = Phi(Lm^T * Lmbar) -> T1 (lower):  P[i][j] = sum_{k >= i} Lm[k][i] Lmbar[k][j]
         if (active) {
             acc_zero(acc);
