@@ -240,6 +240,7 @@ def main():
     nfev = st[..., S_NFEV_TOTAL].sum()
     flops = nfev * svgp_flops(M, N)
     ok_frac = float((st[..., S_STATUS] == 0).mean())
+    eval_cyc, fit_cyc = st[..., 12].sum(), st[..., 13].sum()
 
     # ---- end-to-end leg: the public API from host DataFrames --------------------------------------------------------
     cells = ["c%d" % i for i in range(N)]
@@ -290,6 +291,9 @@ def main():
             "gene_fits_per_hour_per_gpu": value * 3600 / world,
             "elbo_grad_evals_per_sec": float(nfev) * world / T,
             "evals_per_gene": float(nfev) / (G * args.steps), "fit_ok_fraction": ok_frac,
+            "time_split": {"eval_share_of_fit_cycles": float(eval_cyc / fit_cyc),
+                           "us_per_eval_in_fit": float(eval_cyc / nfev / (clocks.get("sm_mhz") or 1965.0)),
+                           "slot_busy_fraction": float(fit_cyc / ((clocks.get("sm_mhz") or 1965.0) * 1e3 * float(np.sum(kern_ms)) * min(engine.default_slots(models), G)))},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": dgemm_tf, "unit": "TFLOP/s",
                          "frac": achieved / dgemm_tf, "traffic": traffic,
                          "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has HBM and bf16 only; "

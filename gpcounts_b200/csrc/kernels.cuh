@@ -124,6 +124,8 @@ __device__ bool fit_one(const FitArgs& a, int g, int k, double prev_alpha, const
     double* st = a.stats + ((size_t)g * a.n_models + k) * GPC_NSTAT;
     const int max_restart = md.restart ? GPC_MAX_RESTART : 0;
     int nfev_total = 0;
+    long long eval_cycles = 0;
+    const long long t_start = clock64();
     OptResult r;
     int attempt = 0;
     bool ok = false;
@@ -154,6 +156,7 @@ __device__ bool fit_one(const FitArgs& a, int g, int k, double prev_alpha, const
         if (a.trace && g == a.trace_gene && k == a.trace_model && attempt == 0) { tr.buf = a.trace; tr.cap = a.trace_cap; }
         r = lbfgsb_minimize(md, Z, y, scale, a.opt, ws, sm, os, &tr);
         nfev_total += r.nfev;
+        eval_cycles += r.eval_cycles;
         ok = (r.task == TASK_PGTOL || r.task == TASK_FTOL);
         if (ok || attempt >= max_restart) break;
     }
@@ -170,7 +173,9 @@ __device__ bool fit_one(const FitArgs& a, int g, int k, double prev_alpha, const
         st[GPC_S_NFEV_TOTAL] = nfev_total;
         st[GPC_S_GNORM] = r.gnorm;
         st[GPC_S_TASK] = r.task;
-        for (int q = 12; q < GPC_NSTAT; ++q) st[q] = 0.0;
+        st[GPC_S_EVAL_CYCLES] = (double)eval_cycles;
+        st[GPC_S_FIT_CYCLES] = (double)(clock64() - t_start);
+        for (int q = 14; q < GPC_NSTAT; ++q) st[q] = 0.0;
     }
     if (a.theta_out) {
         double* out = a.theta_out + ((size_t)g * a.n_models + k) * a.ld_theta;

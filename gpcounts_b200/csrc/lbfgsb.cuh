@@ -290,6 +290,7 @@ struct OptResult {
     int nit, nfev;
     double f;          // final loss (= -ELBO)
     double gnorm;      // max |g|
+    long long eval_cycles;   // SM cycles spent inside model_eval (profiling aid, GPC_S_EVAL_CYCLES)
 };
 
 __device__ __forceinline__ double cta_max(double v, double* red) {
@@ -303,6 +304,23 @@ __device__ __forceinline__ double cta_max(double v, double* red) {
     for (int w = 1; w < GPC_THREADS / 32; ++w) t = fmax(t, red[w]);
     __syncthreads();
     return t;
+}
+
+// Two sums and a maximum over the CTA with one barrier pair; identical results in every thread.
+__device__ __forceinline__ void cta_sum2_max(double& s0, double& s1, double& mx, double* red) {
+    const int NW = GPC_THREADS / 32;
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[warp] = s0; red[NW + warp] = s1; red[2 * NW + warp] = mx; }
+    __syncthreads();
+    double a = 0.0, b = 0.0, c = red[2 * NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) { a += red[w]; b += red[NW + w]; c = fmax(c, red[2 * NW + w]); }
+    __syncthreads();
+    s0 = a; s1 = b; mx = c;
 }
 
 // Optional evaluation trace (debug hook, see gpc_dbg_set_trace): 8 doubles per evaluation.
@@ -329,9 +347,11 @@ __device__ __forceinline__ void trace_eval(OptTrace* tr, double f, double stp, d
 
 // Evaluate loss = -ELBO and its gradient at ws.x; returns status. g is written negated into ws.g.
 __device__ __forceinline__ int eval_loss(const ModelDev& md, const double* Z, const double* y, const double* scale,
-                                         const SlotWs& ws, CtaSmem* sm, double& loss) {
+                                         const SlotWs& ws, CtaSmem* sm, double& loss, long long& cycles) {
     double elbo;
+    const long long t0 = clock64();
     const int st = model_eval(md, Z, y, scale, ws.x, ws.g, &elbo, ws, sm);
+    cycles += clock64() - t0;
     if (st != GPC_ST_OK) return st;
     loss = -elbo;
     return GPC_ST_OK;
@@ -344,9 +364,9 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
     const int P = md.P, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m = opt.m;
     OptResult res;
-    res.nit = 0; res.nfev = 0; res.task = TASK_ABNORMAL; res.f = NAN; res.gnorm = NAN;
+    res.nit = 0; res.nfev = 0; res.task = TASK_ABNORMAL; res.f = NAN; res.gnorm = NAN; res.eval_cycles = 0;
     double f;
-    if (eval_loss(md, Z, y, scale, ws, sm, f) != GPC_ST_OK) { res.task = TASK_CHOL; res.nfev = 1; return res; }
+    if (eval_loss(md, Z, y, scale, ws, sm, f, res.eval_cycles) != GPC_ST_OK) { res.task = TASK_CHOL; res.nfev = 1; return res; }
     int nfev = 1, nit = 0;
     trace_eval(tr, f, 0.0, 0.0, ws.x, ws.g, P, sm->red);
     // g <- -grad(ELBO)
@@ -358,12 +378,23 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
     double theta = 1.0;
     bool updated = false;      // a new pair was stored since the last formk
     while (true) {
-        // ------------------------------------------------------------------ search direction
+        // ------------------------------------------------------------------ search direction (+ line-search set-up)
+        // one pass: d = z - x, dtd, g.d, save (x, g) as (xold, gold); after the first iteration the first trial
+        // point is z itself (stp = 1), so it is written in the same pass
+        double acc2[2] = {0.0, 0.0};
+        const bool first_is_z = nit > 0;
         if (col == 0) {
             for (int i = tid; i < P; i += GPC_THREADS) {
-                const double zi = ws.x[i] - ws.g[i] / theta;
+                const double xi = ws.x[i], gi = ws.g[i];
+                const double zi = xi - gi / theta;
+                const double di = zi - xi;
                 ws.z[i] = zi;
-                ws.d[i] = zi - ws.x[i];
+                ws.d[i] = di;
+                ws.xold[i] = xi;
+                ws.gold[i] = gi;
+                if (first_is_z) ws.x[i] = zi;
+                acc2[0] = fma(di, di, acc2[0]);
+                acc2[1] = fma(gi, di, acc2[1]);
             }
         } else {
             if (warp == 0) {
@@ -384,29 +415,28 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
             __syncthreads();
             if (info != 0) { col = 0; head = 0; theta = 1.0; updated = false; continue; }   // refresh the memory
             updated = false;
+            const double ith = 1.0 / theta;
             for (int i = tid; i < P; i += GPC_THREADS) {
-                double di = -ws.g[i];
+                const double xi = ws.x[i], gi = ws.g[i];
+                double di = -gi;
                 for (int j = 0; j < col; ++j) {
                     const size_t slot = (size_t)((head + j) % m) * P;
                     di += ws.WY[slot + i] * (os->wv[j] / theta) + ws.WS[slot + i] * os->wv[col + j];
                 }
-                di *= 1.0 / theta;
-                const double zi = ws.x[i] + di;
+                di *= ith;
+                const double zi = xi + di;
+                di = zi - xi;
                 ws.z[i] = zi;
-                ws.d[i] = zi - ws.x[i];
+                ws.d[i] = di;
+                ws.xold[i] = xi;
+                ws.gold[i] = gi;
+                if (first_is_z) ws.x[i] = zi;
+                acc2[0] = fma(di, di, acc2[0]);
+                acc2[1] = fma(gi, di, acc2[1]);
             }
         }
-        __syncthreads();
-        // ------------------------------------------------------------------ line search (lnsrlb)
-        double acc2[2] = {0.0, 0.0};
-        for (int i = tid; i < P; i += GPC_THREADS) {
-            const double di = ws.d[i];
-            acc2[0] = fma(di, di, acc2[0]);
-            acc2[1] = fma(ws.g[i], di, acc2[1]);
-            ws.xold[i] = ws.x[i];
-            ws.gold[i] = ws.g[i];
-        }
         cta_sum_n<2>(acc2, sm->red);
+        // ------------------------------------------------------------------ line search (lnsrlb)
         const double dtd = acc2[0];
         const double dnorm = sqrt(dtd);
         double gd = acc2[1];
@@ -414,6 +444,7 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
         const double fold = f;
         double stp = (nit == 0) ? fmin(1.0 / dnorm, LS_STPMAX) : 1.0;
         bool ls_failed = false;
+        double gmax = 0.0, rr = 0.0;
         DcsrchState ls;
         if (!(gd < 0.0) || !dcsrch_start(ls, f, gd, stp)) {
             ls_failed = true;                      // ascent direction in projection (info = -4)
@@ -423,18 +454,30 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
                 stp = ls.stp;
                 ++ifun;
                 ++nfev;
-                if (stp == 1.0) {
-                    for (int i = tid; i < P; i += GPC_THREADS) ws.x[i] = ws.z[i];
-                } else {
-                    for (int i = tid; i < P; i += GPC_THREADS) ws.x[i] = stp * ws.d[i] + ws.xold[i];
+                if (!(ifun == 1 && first_is_z)) {
+                    if (stp == 1.0) {
+                        for (int i = tid; i < P; i += GPC_THREADS) ws.x[i] = ws.z[i];
+                    } else {
+                        for (int i = tid; i < P; i += GPC_THREADS) ws.x[i] = stp * ws.d[i] + ws.xold[i];
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
-                if (eval_loss(md, Z, y, scale, ws, sm, f) != GPC_ST_OK) {
+                if (eval_loss(md, Z, y, scale, ws, sm, f, res.eval_cycles) != GPC_ST_OK) {
                     res.task = TASK_CHOL; res.nit = nit; res.nfev = nfev; return res;
                 }
-                double a = 0.0;
-                for (int i = tid; i < P; i += GPC_THREADS) { const double v = -ws.g[i]; ws.g[i] = v; a = fma(v, ws.d[i], a); }
-                gd = cta_sum(a, sm->red);
+                // one pass: g <- -grad, g.d, max|g|, |g - gold|^2
+                double a3[2] = {0.0, 0.0};
+                double mx = 0.0;
+                for (int i = tid; i < P; i += GPC_THREADS) {
+                    const double v = -ws.g[i];
+                    ws.g[i] = v;
+                    a3[0] = fma(v, ws.d[i], a3[0]);
+                    const double r = v - ws.gold[i];
+                    a3[1] = fma(r, r, a3[1]);
+                    mx = fmax(mx, fabs(v));
+                }
+                cta_sum2_max(a3[0], a3[1], mx, sm->red);
+                gd = a3[0]; rr = a3[1]; gmax = mx;
                 trace_eval(tr, f, stp, gd, ws.x, ws.g, P, sm->red);
                 const int t = dcsrch_step(ls, f, gd);
                 if (t != 0) break;
@@ -452,27 +495,17 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
         stp = ls.stp;
         ++nit;
         // ------------------------------------------------------------------ limits and convergence tests
-        gmax = 0.0;
-        for (int i = tid; i < P; i += GPC_THREADS) gmax = fmax(gmax, fabs(ws.g[i]));
-        sbgnrm = cta_max(gmax, sm->red);
+        sbgnrm = gmax;
         if (nit >= opt.maxiter || nfev > opt.maxfun) { res.task = TASK_LIMIT; break; }
         if (sbgnrm <= opt.gtol) { res.task = TASK_PGTOL; break; }
         if ((fold - f) <= opt.ftol * fmax(fmax(fabs(fold), fabs(f)), 1.0)) { res.task = TASK_FTOL; break; }
         // ------------------------------------------------------------------ BFGS update (matupd)
-        double rr = 0.0;
-        for (int i = tid; i < P; i += GPC_THREADS) {
-            const double r = ws.g[i] - ws.gold[i];
-            ws.gold[i] = r;
-            rr = fma(r, r, rr);
-        }
-        rr = cta_sum(rr, sm->red);
         double dr, ddum;
         if (stp == 1.0) {
             dr = gd - gdold;
             ddum = -gdold;
         } else {
             dr = (gd - gdold) * stp;
-            for (int i = tid; i < P; i += GPC_THREADS) ws.d[i] *= stp;
             ddum = -gdold * stp;
         }
         const bool skip = dr <= GPC_EPSMCH * ddum;
@@ -491,8 +524,16 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
                 head = (head + 1) % m;
                 col = m - 1;
             }
+            // one pass: s = stp * d, y = g - gold, stored in the memory and kept in (d, gold) for the dot products
             const size_t slot = (size_t)((head + col) % m) * P;
-            for (int i = tid; i < P; i += GPC_THREADS) { ws.WS[slot + i] = ws.d[i]; ws.WY[slot + i] = ws.gold[i]; }
+            for (int i = tid; i < P; i += GPC_THREADS) {
+                const double si = (stp == 1.0) ? ws.d[i] : ws.d[i] * stp;
+                const double yi = ws.g[i] - ws.gold[i];
+                ws.d[i] = si;
+                ws.gold[i] = yi;
+                ws.WS[slot + i] = si;
+                ws.WY[slot + i] = yi;
+            }
             ++col;
             theta = rr / dr;
             updated = true;

@@ -57,7 +57,9 @@ enum {
     GPC_S_VAR = 5, GPC_S_LS = 6, GPC_S_ALPHA = 7, GPC_S_KM = 8,   /* fitted hyper-parameters     */
     GPC_S_NFEV_TOTAL = 9,/* evaluations over all attempts (FLOP accounting)                      */
     GPC_S_GNORM = 10,    /* ||grad||_inf at the returned point                                   */
-    GPC_S_TASK = 11      /* optimiser exit: 0 pgtol, 1 ftol, 2 maxiter/maxfun, 3 abnormal line search, 4 Cholesky */
+    GPC_S_TASK = 11,     /* optimiser exit: 0 pgtol, 1 ftol, 2 maxiter/maxfun, 3 abnormal line search, 4 Cholesky */
+    GPC_S_EVAL_CYCLES = 12, /* SM clock cycles spent in ELBO+gradient evaluations (all attempts)            */
+    GPC_S_FIT_CYCLES = 13   /* SM clock cycles of the whole fit of this (gene, model)                       */
 };
 
 /*

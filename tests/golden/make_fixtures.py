@@ -111,6 +111,17 @@ def case_gauss_sparse():
     save("one_sample_sgpr_gauss", X=X, Y=Y, M=M, lik="Gaussian", **res)
 
 
+def case_c5_sample():
+    """48 genes of the headline benchmark workload (bench.py generator, N = 1000, M = 64)."""
+    sys.path.insert(0, ROOT)
+    from bench import synth_batch
+    D, N, M = 48, 1000, 64
+    X, Y = synth_batch(D, N, seed=1234)
+    res = run_tests(dict(X=X, Y=Y, sparse=True, M=M, inducing_variance=1.0), "one_sample_test",
+                    ("Negative_binomial",), D)
+    save("c5_sample_sparse_nb", X=X, Y=Y, M=M, lik="Negative_binomial", **res)
+
+
 def case_branching():
     N, bins = 40, 5
     rng = np.random.default_rng(7)
@@ -163,6 +174,7 @@ CASES = {
     "two_samples": case_two_samples,
     "gauss": case_gauss,
     "gauss_sparse": case_gauss_sparse,
+    "c5_sample": case_c5_sample,
     "branching": case_branching,
     "mouseob": case_mouseob,
 }

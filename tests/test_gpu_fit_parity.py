@@ -172,3 +172,41 @@ def test_mouseob_golden():
     sel = ok & stable
     sel[1] = False      # Slc1a3's dynamic fit is chaotic at round-off level in the reference itself
     assert np.all(np.abs(got[sel, 2] - paper[sel]) <= 2e-3), (got[:, 2], paper)
+
+
+def test_c5_headline_sample():
+    """48 genes of the benchmark workload itself (N = 1000, M = 64, sparse NB One_sample_test).
+
+    On this workload more than half of the *dynamic* fits are round-off-unstable in the oracle itself (constant genes
+    whose RBF fit drifts along a flat valley for 300-1000 iterations: the oracle's two runs differ by up to 1 nat,
+    tests/golden/make_fixtures.py), so the criteria are: (1) constant fits and short, well-posed dynamic fits match
+    tightly (LLR 1e-4 relative, north_star); (2) every LLR stays inside the envelope of the oracle's own
+    variability; (3) >= 99 % agreement of the differential-expression calls at q < 0.05 (north_star)."""
+    from gpcounts_b200 import Fit_GPcounts, host
+    fx = _load("c5_sample_sparse_nb")
+    Xdf, Ydf, _ = _frames(fx)
+    gp = Fit_GPcounts(Xdf, Ydf, sparse=True, M=int(fx["M"]))
+    df = gp.One_sample_test("Negative_binomial")
+    got, ref, ref2 = df.values, fx["ll"], fx["ll_pert"]
+    assert (gp.fit_stats["status"] == 0).all()
+    # (1a) constant fits
+    cst = np.abs(ref[:, 1] - ref2[:, 1]) <= 1e-6 * np.abs(ref[:, 1])
+    assert cst.sum() >= 45
+    assert np.all(np.abs(got[cst, 1] - ref[cst, 1]) <= LL_RTOL * np.abs(ref[cst, 1]))
+    # (1b) well-posed dynamic fits: short in both oracle runs and reproduced by the oracle itself
+    well = (fx["nit"][:, 0] <= 150) & (fx["nit_pert"][:, 0] <= 150) & cst & \
+           (np.abs(ref[:, 0] - ref2[:, 0]) <= 1e-6 * np.abs(ref[:, 0]))
+    assert well.sum() >= 8, well.sum()
+    assert np.all(np.abs(got[well, 0] - ref[well, 0]) <= LL_RTOL * np.abs(ref[well, 0])), (got[well, 0], ref[well, 0])
+    assert np.all(np.abs(got[well, 2] - ref[well, 2]) <= LLR_RTOL * np.abs(ref[well, 2]) + LLR_ATOL)
+    # (2) all genes: inside the envelope of the oracle's own run-to-run variability
+    spread = np.abs(ref[:, 2] - ref2[:, 2])
+    err = np.abs(got[:, 2] - ref[:, 2])
+    assert err.max() <= max(1.5 * spread.max(), 0.5), (err.max(), spread.max())
+    assert np.median(err) <= max(3 * np.median(spread), 2e-3), (np.median(err), np.median(spread))
+    # (3) differential-expression calls
+    q = host.qvalue(host.p_values(np.maximum(got[:, 2], 0)))
+    q_ref = host.qvalue(host.p_values(np.maximum(ref[:, 2], 0)))
+    agree = ((q < 0.05) == (q_ref < 0.05)).mean()
+    assert agree >= 0.99, agree
+    assert (q_ref < 0.05).sum() >= 10
