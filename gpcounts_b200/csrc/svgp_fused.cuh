@@ -195,11 +195,14 @@ __device__ void fz_tri_inverse(const double* L, int n, double* X) {
 // Mirrors lik_point() in lik.cuh (same formulas, same order inside a node).
 struct LikPart { double ve, gm, gz, da, dk; bool poison; };
 
-__device__ __forceinline__ LikPart lik_nodes(const LikParams& lp, double fm, double sd, double y, double logs, int i0,
-                                             int istep) {
+template <int ISTEP>
+__device__ __forceinline__ LikPart lik_nodes(const LikParams& lp, double fm, double sd, double y, double logs, int i0) {
     LikPart o{0.0, 0.0, 0.0, 0.0, 0.0, false};
     const double alpha = lp.alpha, k = lp.k, ia = k, ia2 = k * k, km = lp.km;
-    for (int i = i0; i < GPC_NGH; i += istep) {
+#pragma unroll
+    for (int t = 0; t < (GPC_NGH + ISTEP - 1) / ISTEP; ++t) {
+        const int i = i0 + t * ISTEP;
+        if (i >= GPC_NGH) break;
         const double z = c_gh_z[i], w = c_gh_w[i];
         if (lp.lik == GPC_NB) {
             const double logm = fm + sd * z + logs;
@@ -367,11 +370,15 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
         {
             const int c = tid / FZ_LPC, part = tid % FZ_LPC;
             double s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            for (int i = part; i < Mp; i += FZ_LPC) {
-                const double a = fs->T1[i * FZ_LD + c], b = fs->T2[i * FZ_LD + c];
-                s1 = fma(a, fs->qmu[i], s1);
-                s2 = fma(a, a, s2);
-                s3 = fma(b, b, s3);
+#pragma unroll
+            for (int t = 0; t < FZ_RPT; ++t) {
+                const int i = part + FZ_LPC * t;
+                if (i < Mp) {
+                    const double a = fs->T1[i * FZ_LD + c], b = fs->T2[i * FZ_LD + c];
+                    s1 = fma(a, fs->qmu[i], s1);
+                    s2 = fma(a, a, s2);
+                    s3 = fma(b, b, s3);
+                }
             }
 #pragma unroll
             for (int o = 1; o < FZ_LPC; o <<= 1) {
@@ -392,7 +399,7 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
                     }
                 } else {
                     const double sd = sqrt(fv);
-                    const LikPart o = lik_nodes(lp, fm, sd, yy, log(fs->col[5][c]), part, FZ_LPC);
+                    const LikPart o = lik_nodes<FZ_LPC>(lp, fm, sd, yy, log(fs->col[5][c]), part);
                     ve = o.ve; gm = o.gm; gz = o.gz; da = o.da; dk = o.dk; poison = o.poison;
                     // the node-independent lgamma / digamma terms go to the lanes with the fewest nodes
                     const bool has_const = (md.lik == GPC_NB) || (yy != 0.0);
