@@ -62,18 +62,20 @@ static const double H_GH_W[GPC_NGH] = {
 
 static size_t smem_bytes() { return eval_smem_bytes() + sizeof(OptSmem); }
 
-// Kernel instantiations.  Only the 256-thread one is built: a 512-thread, fused-evaluator-only instantiation
-// (kernels.cuh supports it through GPC_THREADS / GPC_FUSED_ONLY) was measured slower on B200 (494 vs 452 us per
-// C5 evaluation) because its 128-register cap spills the evaluator's accumulators - see DESIGN.md.
-static VariantOps g_ops[1];
+// Kernel instantiations (kernels.cuh): [0] every evaluator, one CTA per SM; [1] dense evaluators only, two CTAs per SM.
+static VariantOps g_ops[2];
+VariantOps gpc_variant_ops_d128();     // gpc_dense.cu
+static int g_force_variant = -1;       // A/B measurements: GPC_FORCE_VARIANT=0 keeps everything on instantiation [0]
 
 static bool host_use_fused(const gpc_model_t& md) {
     return md.kind == GPC_SVGP && md.M <= 64 && md.d <= 2 && md.kernel != GPC_BRANCH;
 }
 
 static int pick_variant(const gpc_model_t* models, int n_models) {
-    (void)models; (void)n_models; (void)host_use_fused;
-    return 0;
+    bool any_fused = false;
+    for (int k = 0; k < n_models; ++k) any_fused = any_fused || host_use_fused(models[k]);
+    if (g_force_variant == 0) return 0;
+    return any_fused ? 0 : 1;
 }
 
 static int ensure_init() {
@@ -85,7 +87,10 @@ static int ensure_init() {
     const double s2 = 1.4142135623730951, sp = 1.7724538509055159;
     for (int i = 0; i < GPC_NGH; ++i) { z[i] = H_GH_X[i] * s2; w[i] = H_GH_W[i] / sp; }
     g_ops[0] = gpc_variant_ops_t256();
-    for (int v = 0; v < 1; ++v)
+    g_ops[1] = gpc_variant_ops_d128();
+    const char* fv = getenv("GPC_FORCE_VARIANT");
+    if (fv) g_force_variant = atoi(fv);
+    for (int v = 0; v < 2; ++v)
         if (g_ops[v].upload_constants(z, w) != 0)
             return set_err(GPC_E_LAUNCH, "constant upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     cudaFuncSetAttribute(k_dbg_linalg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes());

@@ -1,9 +1,12 @@
 // Persistent per-gene kernels (fit and fixed-theta evaluation) and their launchers.
 //
-// This header is compiled twice: with 256 threads per CTA and every evaluator (gpc_api.cu), and with 512 threads per
-// CTA restricted to the fused on-chip SVGP evaluator (gpc_t512.cu, GPC_FUSED_ONLY) - sixteen warps hide the FP64
-// dependency latencies of that evaluator about twice as well as eight, but cap the kernel at 128 registers, which the
-// dense evaluators do not fit.  GPC_KNAME() gives the two instantiations distinct kernel names.
+// This header is compiled twice with different macros (GPC_KNAME() gives the instantiations distinct kernel names):
+//   t256  (gpc_api.cu)   every evaluator, 224 KB of shared memory, one CTA per SM - the fused SVGP path lives here
+//   d128  (gpc_dense.cu) GPC_DENSE_ONLY, __launch_bounds__(256, 2): the dense evaluators need only ~60 KB of shared
+//         memory, so capping them at 128 registers lets two CTAs share an SM and hide each other's global-load
+//         latency; used when no model of a call takes the fused path.
+// (A 512-thread, fused-only instantiation - GPC_THREADS=512, GPC_FUSED_ONLY - was measured slower: 494 vs 452 us per
+// C5 evaluation, its 128-register cap spills the evaluator's accumulators.)
 #pragma once
 #include <algorithm>
 #include <math.h>
@@ -107,8 +110,16 @@ struct FitArgs {
 extern __shared__ __align__(16) unsigned char g_smem[];
 
 // The dense (CtaSmem) and fused (FusedSmem) evaluators overlay the same shared-memory region.
+#ifndef GPC_MIN_BLOCKS
+#define GPC_MIN_BLOCKS 1
+#endif
+
 __host__ __device__ constexpr size_t eval_smem_bytes() {
+#ifdef GPC_DENSE_ONLY
+    return (sizeof(CtaSmem) + 15) & ~(size_t)15;
+#else
     return ((sizeof(CtaSmem) > sizeof(FusedSmem) ? sizeof(CtaSmem) : sizeof(FusedSmem)) + 15) & ~(size_t)15;
+#endif
 }
 
 __device__ __forceinline__ double softplus_inv_d(double p) { return p + log(-expm1(-p)); }
@@ -185,7 +196,7 @@ __device__ bool fit_one(const FitArgs& a, int g, int k, double prev_alpha, const
     return ok;
 }
 
-__global__ void __launch_bounds__(GPC_THREADS) GPC_KNAME(k_fit)(FitArgs a) {
+__global__ void __launch_bounds__(GPC_THREADS, GPC_MIN_BLOCKS) GPC_KNAME(k_fit)(FitArgs a) {
     CtaSmem* sm = reinterpret_cast<CtaSmem*>(g_smem);
     OptSmem* os = reinterpret_cast<OptSmem*>(g_smem + eval_smem_bytes());
     __shared__ int s_job;
@@ -233,7 +244,7 @@ struct EvalArgs {
     WsLayout lay;
 };
 
-__global__ void __launch_bounds__(GPC_THREADS) GPC_KNAME(k_elbo_grad)(EvalArgs a) {
+__global__ void __launch_bounds__(GPC_THREADS, GPC_MIN_BLOCKS) GPC_KNAME(k_elbo_grad)(EvalArgs a) {
     CtaSmem* sm = reinterpret_cast<CtaSmem*>(g_smem);
     __shared__ int s_job;
     const SlotWs ws = carve(a.ws + (size_t)blockIdx.x * a.lay.slot, a.lay);

@@ -521,8 +521,10 @@ __device__ int model_eval(const ModelDev& md, const double* Z, const double* y, 
 #ifdef GPC_FUSED_ONLY
     return eval_svgp_fused(md, Z, y, scale, theta, grad, f_out, ws, reinterpret_cast<FusedSmem*>(sm));
 #else
+#ifndef GPC_DENSE_ONLY
     if (use_fused(md))
         return eval_svgp_fused(md, Z, y, scale, theta, grad, f_out, ws, reinterpret_cast<FusedSmem*>(sm));
+#endif
     switch (md.kind) {
         case GPC_VGP: return eval_vgp(md, y, scale, theta, grad, f_out, ws, sm);
         case GPC_SVGP: return eval_svgp(md, Z, y, scale, theta, grad, f_out, ws, sm);

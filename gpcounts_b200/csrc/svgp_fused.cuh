@@ -131,34 +131,44 @@ __device__ __forceinline__ void acc_store(const double (&acc)[8][2], double* C, 
 }
 
 // Cholesky of the n x n SPD matrix in smem D (ld FZ_LD, lower part used), result in the lower triangle of D.
-// Right-looking with ONE barrier per column: the trailing update of column j reads the *unscaled* column j
-// (D[i][j] D[c][j] / d_jj) while the scaled column is written to its final place by the threads that own it.
+// Left-looking, four lanes per row: lane q of row i keeps the entries l_ik with k = q (mod 4) in registers, so an
+// element is produced by one dot product (no read-modify-write of the trailing matrix).  Every row group recomputes
+// the pivot d_jj = a_jj - sum_k l_jk^2 from row j in shared memory, which leaves ONE barrier per column.
 __device__ bool fz_chol(double* D, int n) {
     const int tid = threadIdx.x;
+    const int i = tid >> 2, q = tid & 3;          // row, lane within the row group (rows >= 64 idle when GPC_THREADS > 256)
+    double lk[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) lk[t] = 0.0;
+    bool ok = true;
     for (int j = 0; j < n; ++j) {
         __syncthreads();
-        const double djj = D[j * FZ_LD + j];
-        if (!(djj > 0.0)) return false;
-        const double inv = 1.0 / djj;
-        // trailing update with the unscaled column j (entries (i, c), j < c <= i); columns are scaled at the end.
-        // thread (row = tid >> 2, q = tid & 3) walks its row in steps of 4
-        const int i = tid >> 2;
-        if (i > j && i < n) {
-            const double lij = -D[i * FZ_LD + j] * inv;
-            for (int c = j + 1 + (tid & 3); c <= i; c += 4)
-                D[i * FZ_LD + c] = fma(lij, D[c * FZ_LD + j], D[i * FZ_LD + c]);
+        // partial sums over k = q, q+4, ... < j of l_jk^2 (pivot) and l_ik l_jk (this row)
+        double pj = 0.0, pi = 0.0;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int k = q + 4 * t;
+            if (k < j) {
+                const double ljk = D[j * FZ_LD + k];
+                pj = fma(ljk, ljk, pj);
+                pi = fma(lk[t], ljk, pi);
+            }
+        }
+        pj += __shfl_xor_sync(0xffffffffu, pj, 1); pj += __shfl_xor_sync(0xffffffffu, pj, 2);
+        pi += __shfl_xor_sync(0xffffffffu, pi, 1); pi += __shfl_xor_sync(0xffffffffu, pi, 2);
+        const double djj = D[j * FZ_LD + j] - pj;
+        if (!(djj > 0.0)) { ok = false; break; }   // uniform: every thread evaluates the same pivot
+        const double ljj = sqrt(djj);
+        if (i < n && i >= j) {
+            const double lij = (i == j) ? ljj : (D[i * FZ_LD + j] - pi) / ljj;
+#pragma unroll
+            for (int t = 0; t < 16; ++t)
+                if (q + 4 * t == j) lk[t] = lij;
+            if (q == 0) D[i * FZ_LD + j] = lij;    // column j of row i is final
         }
     }
     __syncthreads();
-    // scale the columns: L[i][j] = D[i][j] / sqrt(d_jj), L[j][j] = sqrt(d_jj)   (d_jj = final pivot values on the diagonal)
-    for (int idx = tid; idx < n * n; idx += GPC_THREADS) {
-        const int i = idx / n, j = idx % n;
-        if (j < i) D[i * FZ_LD + j] = D[i * FZ_LD + j] / sqrt(D[j * FZ_LD + j]);
-    }
-    __syncthreads();
-    if (tid < n) D[tid * FZ_LD + tid] = sqrt(D[tid * FZ_LD + tid]);
-    __syncthreads();
-    return true;
+    return ok;
 }
 
 // X (smem, 64 x 64, ld FZ_LD) <- inverse of the lower-triangular n x n matrix L (smem), identity-padded to 64.

@@ -48,8 +48,8 @@ def _check_table(df, fx, K, skip=None):
             n_stable += int(stable)
             if skip is not None and (g, k) in skip:
                 continue
-            # unstable fits (the oracle's own two runs disagree): chaotic at round-off level, 1e-4 relative
-            tol = LL_RTOL * abs(a) if stable else max(10.0 * abs(a - b), 1e-4 * abs(a))
+            # unstable fits (the oracle's own two runs disagree): plateau stops, chaotic at round-off level - 3e-4 relative
+            tol = LL_RTOL * abs(a) if stable else max(10.0 * abs(a - b), 3e-4 * abs(a))
             assert abs(got[g, k] - a) <= tol, (g, k, got[g, k], a, b)
         a, b = ref[g, K], ref2[g, K]
         if skip is not None and any(gg == g for gg, _ in skip):
