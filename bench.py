@@ -5,7 +5,7 @@
 
 Workload (BASELINE.json configs[4], the configuration the metric is quoted on): synthetic C5 generator
  - N = 1000 spots, sparse NB with M = 64 inducing points, One_sample_test (dynamic RBF fit +
-constant fit + LLR per gene).  A *step* fits one fresh batch of G genes per GPU (default 4096) drawn from that
+constant fit + LLR per gene).  A *step* fits one fresh batch of G genes per GPU (default 8192) drawn from that
 generator; value = genes fitted per second over all GPUs with the batch resident in HBM, e2e = the same through
 ``Fit_GPcounts(...).One_sample_test`` from host DataFrames (H2D / D2H inside the timed region).
 Under torchrun every rank fits its own batches (weak scaling, no data-path collective); time = max over ranks.
@@ -164,7 +164,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--genes", type=int, default=4096, help="genes per step per GPU")
+    ap.add_argument("--genes", type=int, default=8192, help="genes per step per GPU")
     ap.add_argument("--N", type=int, default=1000)
     ap.add_argument("--M", type=int, default=64)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -294,10 +294,12 @@ def main():
             "time_split": {"eval_share_of_fit_cycles": float(eval_cyc / fit_cyc),
                            "us_per_eval_in_fit": float(eval_cyc / nfev / (clocks.get("sm_mhz") or 1965.0)),
                            "slot_busy_fraction": float(fit_cyc / ((clocks.get("sm_mhz") or 1965.0) * 1e3 * float(np.sum(kern_ms)) * min(engine.default_slots(models), G)))},
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": dgemm_tf, "unit": "TFLOP/s",
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": dgemm_tf, "unit": "TFLOP/s",
                          "frac": achieved / dgemm_tf, "traffic": traffic,
-                         "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has HBM and bf16 only; "
-                                        "DFMA/DMMA microbenchmark: profiles/r01_fp64_peak.txt)",
+                         "pipe": "FP64 tensor pipe (DMMA.8x8x4; tcgen05 has no FP64 kind)",
+                         "peak_source": "FP64: cuBLAS DGEMM 4096^3 measured in this run - MEASURED_PEAKS.json holds HBM and "
+                                        "bf16 only, so the FP64 denominator is measured here (DFMA 35.7 / DMMA 37.1 TFLOP/s "
+                                        "microbenchmark: profiles/r01_fp64_peak.txt)",
                          "algorithmic_flops_per_eval": svgp_flops(M, N), "kernel": "k_fit (one launch per step)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d / e2e_steps),
                     "d2h_bytes_per_step": int(d2h / e2e_steps), "steps": e2e_steps},
