@@ -260,7 +260,7 @@ def main():
         torch.cuda.synchronize(dev)
         e2e_T += time.time() - t0
         h2d += Y.nbytes + G * 2 * 4 * 8 + X.nbytes + Zsets.nbytes + 2 * rtab.nbytes
-        d2h += G * 2 * 16 * 8 + G * 2 * (4 + M + M * (M + 1) // 2) * 8
+        d2h += G * 2 * 16 * 8 + (4 + M + M * (M + 1) // 2) * 8      # statistics rows + fitted parameters of the last gene
     if world > 1:
         t = torch.tensor([e2e_T], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

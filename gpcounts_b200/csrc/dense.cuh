@@ -17,7 +17,7 @@
 #endif
 #define GPC_BLK 64                 // block size of the blocked factorisations (= GEMM tile edge)
 #define GPC_BK 16                 // GEMM k-panel
-#define GPC_LDS 66                // padded leading dimension of the staged GEMM panels
+#define GPC_LDS 68                // padded leading dimension of the staged GEMM panels (== 4 mod 16: conflict-free DMMA fragments)
 #define GPC_LDD 65                // padded leading dimension of the 64x64 diagonal block in smem
 
 enum { F_A_LOWER = 1, F_A_UPPER = 2, F_B_LOWER = 4, F_B_UPPER = 8, F_C_LOWER = 16 };
@@ -77,14 +77,21 @@ __device__ __forceinline__ void cta_sum_n(double (&v)[K], double* red) {
 //        F_C_LOWER              only entries j <= i are computed and stored
 // In-place use (C aliasing an operand) is safe when the aliased operand region of every output tile is
 // that tile itself (single tile along the shared dimension), because all loads of a tile precede its stores.
+__device__ __forceinline__ void dense_dmma884(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// Inner product of a 64 x 64 output tile on the FP64 tensor pipe: warp w owns rows 8w..8w+7 (eight 8 x 8 DMMA tiles);
+// the k-panels (16 deep) are staged k-major in shared memory and the global loads of the next panel are issued
+// before the current one is multiplied (register prefetch).
 template <bool TA, bool TB>
 __device__ __noinline__ void cta_gemm(int m, int n, int k, double alpha, const double* __restrict__ A, int lda,
                          const double* __restrict__ B, int ldb, double beta, double* C, int ldc, int flags,
                          CtaSmem* sm) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int row0 = (warp >> 2) * 32 + (lane >> 2) * 4;
-    const int col0 = (warp & 3) * 16 + (lane & 3) * 4;
+    const int ar = lane >> 2, ak = lane & 3;
     double* As = sm->panelA;
     double* Bs = sm->panelB;
     for (int i0 = 0; i0 < m; i0 += 64) {
@@ -96,71 +103,95 @@ __device__ __noinline__ void cta_gemm(int m, int n, int k, double alpha, const d
             if (flags & F_A_LOWER) kmax = min(kmax, i0 + 64);
             if (flags & F_B_UPPER) kmax = min(kmax, j0 + 64);
             kmin &= ~(GPC_BK - 1);
-            double acc[4][4];
+            double acc[8][2];
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+            for (int t = 0; t < 8; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+            double ra0, ra1, ra2, ra3, rb0, rb1, rb2, rb3;
+            const bool warp_rows_valid = i0 + warp * 8 < m && (!(flags & F_C_LOWER) || j0 <= i0 + warp * 8 + 7);
+            const int nct = min(8, (n - j0 + 7) >> 3);
+#define GPC_LOAD_A(dst, e, K0)                                                                         \
+            {                                                                                          \
+                const int idx = tid + (e) * GPC_THREADS;                                               \
+                int ii, kk;                                                                            \
+                if (!TA) { kk = idx & 15; ii = idx >> 4; } else { ii = idx & 63; kk = idx >> 6; }      \
+                const int gi = i0 + ii, gk = (K0) + kk;                                                \
+                double v = 0.0;                                                                        \
+                if (gi < m && gk < kmax) {                                                             \
+                    bool ok = true;                                                                    \
+                    if ((flags & F_A_LOWER) && gk > gi) ok = false;                                    \
+                    if ((flags & F_A_UPPER) && gk < gi) ok = false;                                    \
+                    if (ok) v = TA ? A[(size_t)gk * lda + gi] : A[(size_t)gi * lda + gk];              \
+                }                                                                                      \
+                dst = v;                                                                               \
+            }
+#define GPC_LOAD_B(dst, e, K0)                                                                         \
+            {                                                                                          \
+                const int idx = tid + (e) * GPC_THREADS;                                               \
+                int jj, kk;                                                                            \
+                if (!TB) { jj = idx & 63; kk = idx >> 6; } else { kk = idx & 15; jj = idx >> 4; }      \
+                const int gj = j0 + jj, gk = (K0) + kk;                                                \
+                double v = 0.0;                                                                        \
+                if (gj < n && gk < kmax) {                                                             \
+                    bool ok = true;                                                                    \
+                    if ((flags & F_B_LOWER) && gj > gk) ok = false;                                    \
+                    if ((flags & F_B_UPPER) && gj < gk) ok = false;                                    \
+                    if (ok) v = TB ? B[(size_t)gj * ldb + gk] : B[(size_t)gk * ldb + gj];              \
+                }                                                                                      \
+                dst = v;                                                                               \
+            }
+#define GPC_STORE_AB(e, va, vb)                                                                        \
+            {                                                                                          \
+                const int idx = tid + (e) * GPC_THREADS;                                               \
+                int ii, kk, jj, kb;                                                                    \
+                if (!TA) { kk = idx & 15; ii = idx >> 4; } else { ii = idx & 63; kk = idx >> 6; }      \
+                if (!TB) { jj = idx & 63; kb = idx >> 6; } else { kb = idx & 15; jj = idx >> 4; }      \
+                As[kk * GPC_LDS + ii] = va;                                                            \
+                Bs[kb * GPC_LDS + jj] = vb;                                                            \
+            }
+            if (kmin < kmax) {
+                GPC_LOAD_A(ra0, 0, kmin) GPC_LOAD_A(ra1, 1, kmin) GPC_LOAD_A(ra2, 2, kmin) GPC_LOAD_A(ra3, 3, kmin)
+                GPC_LOAD_B(rb0, 0, kmin) GPC_LOAD_B(rb1, 1, kmin) GPC_LOAD_B(rb2, 2, kmin) GPC_LOAD_B(rb3, 3, kmin)
+            }
             for (int k0 = kmin; k0 < kmax; k0 += GPC_BK) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int idx = tid + e * GPC_THREADS;
-                    int ii, kk;
-                    if (!TA) { kk = idx & 15; ii = idx >> 4; } else { ii = idx & 63; kk = idx >> 6; }
-                    const int gi = i0 + ii, gk = k0 + kk;
-                    double v = 0.0;
-                    if (gi < m && gk < kmax) {
-                        bool ok = true;
-                        if ((flags & F_A_LOWER) && gk > gi) ok = false;
-                        if ((flags & F_A_UPPER) && gk < gi) ok = false;
-                        if (ok) v = TA ? A[(size_t)gk * lda + gi] : A[(size_t)gi * lda + gk];
-                    }
-                    As[kk * GPC_LDS + ii] = v;
-                }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int idx = tid + e * GPC_THREADS;
-                    int jj, kk;
-                    if (!TB) { jj = idx & 63; kk = idx >> 6; } else { kk = idx & 15; jj = idx >> 4; }
-                    const int gj = j0 + jj, gk = k0 + kk;
-                    double v = 0.0;
-                    if (gj < n && gk < kmax) {
-                        bool ok = true;
-                        if ((flags & F_B_LOWER) && gj > gk) ok = false;
-                        if ((flags & F_B_UPPER) && gj < gk) ok = false;
-                        if (ok) v = TB ? B[(size_t)gj * ldb + gk] : B[(size_t)gk * ldb + gj];
-                    }
-                    Bs[kk * GPC_LDS + jj] = v;
-                }
+                GPC_STORE_AB(0, ra0, rb0) GPC_STORE_AB(1, ra1, rb1) GPC_STORE_AB(2, ra2, rb2) GPC_STORE_AB(3, ra3, rb3)
                 __syncthreads();
+                if (k0 + GPC_BK < kmax) {
+                    const int kn = k0 + GPC_BK;
+                    GPC_LOAD_A(ra0, 0, kn) GPC_LOAD_A(ra1, 1, kn) GPC_LOAD_A(ra2, 2, kn) GPC_LOAD_A(ra3, 3, kn)
+                    GPC_LOAD_B(rb0, 0, kn) GPC_LOAD_B(rb1, 1, kn) GPC_LOAD_B(rb2, 2, kn) GPC_LOAD_B(rb3, 3, kn)
+                }
+                if (warp_rows_valid) {             // ragged edge tiles: warps / column tiles beyond m, n do no math
 #pragma unroll
-                for (int kk = 0; kk < GPC_BK; ++kk) {
-                    const double2 a01 = *reinterpret_cast<const double2*>(&As[kk * GPC_LDS + row0]);
-                    const double2 a23 = *reinterpret_cast<const double2*>(&As[kk * GPC_LDS + row0 + 2]);
-                    const double2 b01 = *reinterpret_cast<const double2*>(&Bs[kk * GPC_LDS + col0]);
-                    const double2 b23 = *reinterpret_cast<const double2*>(&Bs[kk * GPC_LDS + col0 + 2]);
-                    const double a[4] = {a01.x, a01.y, a23.x, a23.y};
-                    const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+                    for (int kq = 0; kq < GPC_BK; kq += 4) {
+                        const double a = As[(kq + ak) * GPC_LDS + warp * 8 + ar];
 #pragma unroll
-                    for (int r = 0; r < 4; ++r)
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+                        for (int t = 0; t < 8; ++t) {
+                            if (t < nct) {
+                                const double b = Bs[(kq + ak) * GPC_LDS + t * 8 + ar];
+                                dense_dmma884(acc[t], a, b);
+                            }
+                        }
+                    }
                 }
                 __syncthreads();
             }
+#undef GPC_LOAD_A
+#undef GPC_LOAD_B
+#undef GPC_STORE_AB
+            const int gi = i0 + warp * 8 + ar;
+            if (gi < m) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int gi = i0 + row0 + r;
-                if (gi >= m) continue;
+                for (int t = 0; t < 8; ++t) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int gj = j0 + col0 + c;
-                    if (gj >= n) continue;
-                    if ((flags & F_C_LOWER) && gj > gi) continue;
-                    double* p = C + (size_t)gi * ldc + gj;
-                    double v = alpha * acc[r][c];
-                    if (beta != 0.0) v += beta * (*p);
-                    *p = v;
+                    for (int c = 0; c < 2; ++c) {
+                        const int gj = j0 + t * 8 + 2 * ak + c;
+                        if (gj >= n) continue;
+                        if ((flags & F_C_LOWER) && gj > gi) continue;
+                        double* p = C + (size_t)gi * ldc + gj;
+                        double v = alpha * acc[t][c];
+                        if (beta != 0.0) v += beta * (*p);
+                        *p = v;
+                    }
                 }
             }
         }
