@@ -126,7 +126,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = int(args.cpu_genes or max(8, min(2 * cores, 64)))
+    sample = int(args.cpu_genes or max(16, min(4 * cores, 96)))
     times, evals = [], []
     for s in range(args.warmup + args.steps):
         X, Y = synth_batch(sample, args.N, seed=1234 + s)
@@ -309,7 +309,7 @@ def main():
         }
         if not args.no_cpu and world == 1:
             cores = os.cpu_count() or 1
-            sample = int(args.cpu_genes or max(8, min(2 * cores, 64)))
+            sample = int(args.cpu_genes or max(16, min(4 * cores, 96)))
             Ys = batches[args.warmup][0][:sample]
             gps, eps, dt = cpu_one_sample(X, Ys, M, cores)
             line["cpu_baseline"] = {"value": gps, "unit": UNIT, "cores": cores, "kind": "port",

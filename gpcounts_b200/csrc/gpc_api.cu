@@ -62,9 +62,11 @@ static const double H_GH_W[GPC_NGH] = {
 
 static size_t smem_bytes() { return eval_smem_bytes() + sizeof(OptSmem); }
 
-// Kernel instantiations (kernels.cuh): [0] every evaluator, one CTA per SM; [1] dense evaluators only, two CTAs per SM.
-static VariantOps g_ops[2];
+// Kernel instantiations (kernels.cuh): [0] every evaluator; [1] dense evaluators only, two CTAs per SM;
+// [2] fused SVGP evaluator only.
+static VariantOps g_ops[3];
 VariantOps gpc_variant_ops_d128();     // gpc_dense.cu
+VariantOps gpc_variant_ops_f256();     // gpc_fused.cu
 static int g_force_variant = -1;       // A/B measurements: GPC_FORCE_VARIANT=0 keeps everything on instantiation [0]
 
 static bool host_use_fused(const gpc_model_t& md) {
@@ -72,10 +74,14 @@ static bool host_use_fused(const gpc_model_t& md) {
 }
 
 static int pick_variant(const gpc_model_t* models, int n_models) {
-    bool any_fused = false;
-    for (int k = 0; k < n_models; ++k) any_fused = any_fused || host_use_fused(models[k]);
+    bool any_fused = false, all_fused = true;
+    for (int k = 0; k < n_models; ++k) {
+        const bool f = host_use_fused(models[k]);
+        any_fused = any_fused || f;
+        all_fused = all_fused && f;
+    }
     if (g_force_variant == 0) return 0;
-    return any_fused ? 0 : 1;
+    return all_fused ? 2 : (any_fused ? 0 : 1);
 }
 
 static int ensure_init() {
@@ -88,9 +94,10 @@ static int ensure_init() {
     for (int i = 0; i < GPC_NGH; ++i) { z[i] = H_GH_X[i] * s2; w[i] = H_GH_W[i] / sp; }
     g_ops[0] = gpc_variant_ops_t256();
     g_ops[1] = gpc_variant_ops_d128();
+    g_ops[2] = gpc_variant_ops_f256();
     const char* fv = getenv("GPC_FORCE_VARIANT");
     if (fv) g_force_variant = atoi(fv);
-    for (int v = 0; v < 2; ++v)
+    for (int v = 0; v < 3; ++v)
         if (g_ops[v].upload_constants(z, w) != 0)
             return set_err(GPC_E_LAUNCH, "constant upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     cudaFuncSetAttribute(k_dbg_linalg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes());

@@ -1,10 +1,14 @@
 // Persistent per-gene kernels (fit and fixed-theta evaluation) and their launchers.
 //
-// This header is compiled twice with different macros (GPC_KNAME() gives the instantiations distinct kernel names):
-//   t256  (gpc_api.cu)   every evaluator, 224 KB of shared memory, one CTA per SM - the fused SVGP path lives here
+// This header is compiled three times with different macros (GPC_KNAME() gives the instantiations distinct names):
+//   f256  (gpc_fused.cu) GPC_FUSED_ONLY: only the fused on-chip SVGP evaluator (+ optimiser).  Used when every model of
+//         a call takes the fused path - the headline C5 workload.  Keeping the dense call graph out of this
+//         instantiation matters: with it in the same kernel ptxas spilled ~1.5-2 KB per thread in the evaluator
+//         (730 instead of 430 us per evaluation) depending on unrelated changes to the dense code.
 //   d128  (gpc_dense.cu) GPC_DENSE_ONLY, __launch_bounds__(256, 2): the dense evaluators need only ~60 KB of shared
 //         memory, so capping them at 128 registers lets two CTAs share an SM and hide each other's global-load
 //         latency; used when no model of a call takes the fused path.
+//   t256  (gpc_api.cu)   every evaluator, one CTA per SM: calls that mix fused and dense models.
 // (A 512-thread, fused-only instantiation - GPC_THREADS=512, GPC_FUSED_ONLY - was measured slower: 494 vs 452 us per
 // C5 evaluation, its 128-register cap spills the evaluator's accumulators.)
 #pragma once

@@ -37,6 +37,8 @@ struct FusedSmem {
     double red[64];
     double Zs[64 * 2];              // inducing inputs (d <= 2)
     double Xs[64 * 2];              // inputs of the current column tile
+    KernParams kp;                  // per-evaluation constants live here rather than in registers: the evaluator
+    LikParams lp;                   // is register-bound (rank-update accumulators), reloads from smem are cheap
 };
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
@@ -260,19 +262,26 @@ __device__ __forceinline__ LikPart lik_nodes(const LikParams& lp, double fm, dou
 }
 
 // ELBO + gradient of one SVGP gene-model, M <= 64.  Same contract as eval_svgp().
-__device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z, const double* y, const double* scale,
-                               const double* theta, double* grad, double* f_out, const SlotWs& ws, FusedSmem* fs) {
+// The body is force-inlined into its two users: the eval-only kernel (directly) and the out-of-line wrapper
+// eval_svgp_fused() that the fit kernel calls - ptxas register-allocates an out-of-line clone per kernel, and
+// the clone under the small eval-only kernel otherwise ends up with ~1.5 KB of spills.
+__device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const double* Z, const double* y,
+                                                    const double* scale, const double* theta, double* grad,
+                                                    double* f_out, const SlotWs& ws, FusedSmem* fs) {
     const int N = md.N, M = md.M, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nrb = (M + 7) >> 3, Mp = nrb * 8;          // 8-row blocks in use
-    const Hyper h = hyper_from_theta(md, theta);
-    KernParams kp;
-    kern_setup(kp, md, h.var, h.ls);
-    LikParams lp;
-    lik_setup(lp, md.lik, h.alpha, h.km);
+    if (tid == 0) {
+        const Hyper h0 = hyper_from_theta(md, theta);
+        kern_setup(fs->kp, md, h0.var, h0.ls);
+        lik_setup(fs->lp, md.lik, h0.alpha, h0.km);
+    }
+    __syncthreads();
+    const KernParams& kp = fs->kp;
+    const LikParams& lp = fs->lp;
     const double* q_mu = theta + GPC_NHYP;
     const double* lq_packed = theta + GPC_NHYP + M;
     const double shift = md.jitter + (md.kernel == GPC_BRANCH ? GPC_BRANCH_NOISE : 0.0);
-    const double kdiag = h.var + (md.kernel == GPC_BRANCH ? GPC_BRANCH_NOISE : 0.0);
+    const double kdiag = kp.var + (md.kernel == GPC_BRANCH ? GPC_BRANCH_NOISE : 0.0);
     const bool need_kg = (md.train_mask & 3) != 0;
     const int dd = md.d;
 
@@ -597,11 +606,17 @@ __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z,
         }
         cta_sum_n<2>(a2, fs->red);
         // RBF / Constant: d Kuf / d var = Kuf / var, so <S, dKuf/dvar> = <Abar, A> / var
-        gvar = acc6[3] + acc6[4] / h.var + a2[0];
+        gvar = acc6[3] + acc6[4] / kp.var + a2[0];
         if (md.kernel != GPC_CONST) gls = acc6[5] * kp.inv_ls3 + a2[1];
     }
+    const Hyper h = hyper_from_theta(md, theta);
     store_hyper_grad(md, h, gvar, gls, acc6[1], acc6[2], grad);
     *f_out = acc6[0] - kl;
     __syncthreads();
     return GPC_ST_OK;
+}
+
+__device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z, const double* y, const double* scale,
+                               const double* theta, double* grad, double* f_out, const SlotWs& ws, FusedSmem* fs) {
+    return eval_svgp_fused_impl(md, Z, y, scale, theta, grad, f_out, ws, fs);
 }
