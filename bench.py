@@ -280,8 +280,8 @@ def main():
         dgemm_tf = 2 * 4096 ** 3 / best * 1e-9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        if os.path.exists(tp):      # measured per gene on a 148-gene ncu capture, scaled to the genes of one launch
+            traffic = json.load(open(tp)).get("dram_bytes_per_gene", 0.0) * G or None
         achieved = flops / (float(np.sum(kern_ms)) * 1e-3) * 1e-12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
