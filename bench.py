@@ -254,6 +254,7 @@ def main():
         barrier()
         t0 = time.time()
         gp = Fit_GPcounts(Xdf, Ydf, sparse=True, M=M, device=dev)
+        gp.distributed = False          # weak scaling like `value`: every rank pushes its own batch through the API
         gp.optimizer_options = {"maxiter": args.maxiter}
         df = gp.One_sample_test("Negative_binomial")
         llr_sum = float(np.nansum(df["log_likelihood_ratio"].values))     # result read on the host

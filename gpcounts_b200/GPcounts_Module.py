@@ -117,6 +117,7 @@ class Fit_GPcounts(object):
         self.fit_stats = None           # DataFrame: per (gene, model) status / iterations / hyper-parameters
         self.optimizer_options = {}     # overrides of the L-BFGS-B settings (m, maxiter, maxfun, maxls, ftol, gtol)
         self.last_fit_seconds = None
+        self.distributed = True         # shard genes over torch.distributed ranks when a process group is initialised
         if safe_mode:
             raise NotImplementedError(
                 "safe_mode=True (stochastic posterior-predictive local-optimum checks, reference :558-565, "
@@ -265,7 +266,7 @@ class Fit_GPcounts(object):
         from . import engine, sharding
         dev = self._device()
         genes_index = np.asarray(list(genes_index), dtype=np.int64)
-        rank, world = sharding.rank_world()
+        rank, world = sharding.rank_world() if self.distributed else (0, 1)
         mine = sharding.shard_indices(len(genes_index), rank, world)
         gsel = genes_index[mine]
         K = len(models)
