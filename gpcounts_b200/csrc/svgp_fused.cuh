@@ -221,9 +221,10 @@ __device__ __forceinline__ LikPart lik_nodes(const LikParams& lp, double fm, dou
             const double m = exp(logm);
             const double t = 1.0 + m * alpha;
             const double lt = log(t);
+            const double it = 1.0 / t;                       // one reciprocal instead of two FP64 divisions per node
             const double l = y * (logm + lp.log_alpha - lt) - k * lt;
-            const double dl = (y - m) / t;
-            const double dal = y * ia + lt * ia2 - (y + k) * m / t;
+            const double dl = (y - m) * it;
+            const double dal = y * ia + lt * ia2 - (y + k) * (m * it);
             o.ve = fma(w, l, o.ve); o.gm = fma(w, dl, o.gm); o.gz = fma(w * z, dl, o.gz); o.da = fma(w, dal, o.da);
         } else {   // ZINB, see lik.cuh for the reference-faithful psi arithmetic
             const double F = fm + sd * z;
