@@ -155,8 +155,8 @@ def workload_config(args, genes_per_step):
                         "20k-gene generator, step = fresh batch of genes" % (args.N, args.M),
             "genes_per_step_per_gpu": genes_per_step, "N": args.N, "M": args.M, "models_per_gene": 2,
             "optimizer": "L-BFGS-B m=10 ftol=2.22e-9 gtol=1e-5 maxiter=5000 (SciPy defaults of the reference)",
-            "l2_policy": "fresh gene batch every step; per-slot workspace (~%d MB total) exceeds the 126 MB L2"
-                         % int(296 * 3.2)}
+            "l2_policy": "fresh gene batch every step (64 MB of counts) and 148 per-slot workspaces of ~3.2 MB (~470 MB) "
+                         "that every evaluation rewrites: the working set exceeds the 126 MB L2"}
 
 
 def main():

@@ -3,8 +3,7 @@ number is produced by the sm_100a kernels behind ``libgpcounts_b200.so`` (no CPU
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass, field
-from typing import Optional, Sequence
+from typing import Sequence
 
 import numpy as np
 import torch
@@ -109,7 +108,7 @@ def _workspace(nbytes, device):
     return buf
 
 
-def default_slots(models, max_bytes=None):
+def default_slots(models):
     lib = L.load()
     arr = _models_array(models)
     return int(lib.gpc_default_slots(arr, len(models)))
@@ -152,10 +151,10 @@ def fit(models: Sequence[Model], Y, scale, hyp0, chain=True, opt=None, return_th
     arr = _models_array(models)
     n_jobs = D if chain else D * K
     n_slots = n_slots or min(default_slots(models), max(n_jobs, 1))
-    if max_ws_bytes is None:
+    if max_ws_bytes is None:        # 80 % of what is free now, plus what the cached workspace already holds
         free, _total = torch.cuda.mem_get_info(dev)
-        max_ws_bytes = int(free * 0.8) + (_ws_cache.get(torch.device(dev).index or 0).numel()
-                                          if _ws_cache.get(torch.device(dev).index or 0) is not None else 0)
+        cached = _ws_cache.get(torch.device(dev).index or 0)
+        max_ws_bytes = int(free * 0.8) + (cached.numel() if cached is not None else 0)
     while n_slots > 1 and lib.gpc_workspace_bytes(arr, K, C.byref(opt), n_slots) > max_ws_bytes:
         n_slots = max(1, n_slots // 2)
     nbytes = lib.gpc_workspace_bytes(arr, K, C.byref(opt), n_slots)
