@@ -118,6 +118,8 @@ class Fit_GPcounts(object):
         self.optimizer_options = {}     # overrides of the L-BFGS-B settings (m, maxiter, maxfun, maxls, ftol, gtol)
         self.last_fit_seconds = None
         self.distributed = True         # shard genes over torch.distributed ranks when a process group is initialised
+        self.inducing_per_gene = False  # True: attempt 0 uses RobustGP points selected under each gene's own initial
+                                        # variance, as the reference does; default: one shared set
         if safe_mode:
             raise NotImplementedError(
                 "safe_mode=True (stochastic posterior-predictive local-optimum checks, reference :558-565, "
@@ -278,6 +280,12 @@ class Fit_GPcounts(object):
         t1 = torch.cuda.Event(enable_timing=True)
         t0.record(torch.cuda.current_stream(dev))
         if len(gsel):
+            if self.sparse and self.inducing_per_gene:
+                from . import inducing
+                for k, m in enumerate(models):
+                    if m.kernel == "RBF" and self.user_hyper_parameters[1] is None:
+                        Xm = m.X.cpu().numpy()
+                        m.Zgene = inducing.select_per_gene(Xm, m.M, float(hyp0[0, k, 1]), hyp0[gsel, k, 0], dev).contiguous()
             stats, theta = engine.fit(models, np.ascontiguousarray(Yfit[gsel]), scale, hyp0[gsel], chain=chain,
                                       opt=self._opt(), return_theta=True)
         else:
