@@ -96,6 +96,11 @@ def test_sgpr(kernel, M):
     _compare("SGPR", kernel, "GAUSS", N=150, M=M)
 
 
+def test_gpr_branch_kernel():
+    """Gaussian likelihood with the branching kernel (Branching_GPcounts notebook, lik_name="Gaussian")."""
+    _compare("GPR", "BRANCH", "GAUSS", N=60, xp=0.4)
+
+
 def test_per_gene_inducing_points():
     """gpc_model_t.Zgene: every gene evaluates with its own inducing set."""
     from gpcounts_b200 import engine

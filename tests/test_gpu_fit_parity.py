@@ -229,3 +229,34 @@ def test_per_gene_inducing_mode_runs_and_matches_reference_selection():
     # shared-Z and per-gene-Z results differ at most at the level of two equally good inducing sets
     ref = fx["ll"]
     assert np.all(np.abs(df.values[:, 1] - ref[:, 1]) <= 1e-3 * np.abs(ref[:, 1]))
+
+
+def test_failed_fits_follow_the_restart_protocol():
+    """maxiter=1 can never end in CONVERGENCE, so every attempt is `success == False`: the reference restarts ten times
+    from the seeded random hyper-parameters (:699-706, :769-779) and then reports NaN (:533-535, :455-457)."""
+    from gpcounts_b200 import Fit_GPcounts
+    from oracle.fit import OracleFit
+    from tests.helpers import synth_counts
+    X, Y = synth_counts(3, 30, seed=8)
+    cells = ["c%d" % i for i in range(30)]
+    gp = Fit_GPcounts(pd.DataFrame(X, index=cells), pd.DataFrame(Y, index=["a", "b", "c"], columns=cells))
+    gp.optimizer_options = {"maxiter": 1}
+    df = gp.One_sample_test("Negative_binomial")
+    assert df.isna().all().all()
+    st = gp.fit_stats
+    dyn = st[st.model == "dynamic"]
+    assert (dyn.status == 2).all() and (dyn.restarts == 10).all()
+    assert (st[st.model == "constant"].status == 3).all()          # skipped: the dynamic fit failed (:442)
+    o = OracleFit(X, Y, lbfgs_options=dict(maxiter=1))
+    r, _ = o.fit_model(X, Y[0].astype(int).astype(float), None, "NB", 1, 2)
+    assert r.restarts == 10 and np.isnan(r.log_likelihood)
+
+
+def test_branching_gaussian_runs():
+    from gpcounts_b200 import Fit_GPcounts
+    fx = _load("branching_nb")
+    t, labels, Y = fx["t"], fx["labels"], fx["Y"]
+    cells = ["c%d" % i for i in range(len(t))]
+    gp = Fit_GPcounts(pd.DataFrame(t, index=cells), pd.DataFrame(Y, index=["gene"], columns=cells))
+    res = gp.Infer_branching_location(labels, bins_num=5, lik_name="Gaussian")
+    assert np.isfinite(res["loglik"]).all() and abs(res["branching_probability"].sum() - 1) < 1e-12

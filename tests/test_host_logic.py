@@ -33,7 +33,6 @@ def test_restart_table_matches_oracle_restart_path():
     r, _ = o.fit_model(X, Y[0], None, "NB", 1, 1)
     assert r.restarts == 10 and not r.ok
     tab, _ = host.restart_table(X)
-    th = r.spec and r  # last attempt used seed 10
     assert np.isnan(r.log_likelihood)
     assert tab.shape == (10, 4)
 
