@@ -131,7 +131,13 @@ __device__ __forceinline__ double softplus_inv_d(double p) { return p + log(-exp
 // Fit one (gene, model); returns true when the fit succeeded. prev_alpha < 0: no hand-off.
 __device__ bool fit_one(const FitArgs& a, int g, int k, double prev_alpha, const SlotWs& ws, CtaSmem* sm, OptSmem* os,
                         double& alpha_out) {
-    const ModelDev md = a.models[k];
+    // the model descriptor lives in shared memory: it is passed by reference into out-of-line evaluators, and a
+    // per-thread copy would sit in local memory behind an L1 that the 225 KB shared-memory carve-out leaves tiny
+    __shared__ ModelDev s_md;
+    __syncthreads();
+    if (threadIdx.x == 0) s_md = a.models[k];
+    __syncthreads();
+    const ModelDev& md = s_md;
     const int tid = threadIdx.x;
     const double* y = a.Y + (size_t)g * a.ldy + md.n_off;
     const double* scale = a.scale ? a.scale + (size_t)g * a.ldy + md.n_off : nullptr;
@@ -204,7 +210,10 @@ __global__ void __launch_bounds__(GPC_THREADS, GPC_MIN_BLOCKS) GPC_KNAME(k_fit)(
     CtaSmem* sm = reinterpret_cast<CtaSmem*>(g_smem);
     OptSmem* os = reinterpret_cast<OptSmem*>(g_smem + eval_smem_bytes());
     __shared__ int s_job;
-    const SlotWs ws = carve(a.ws + (size_t)blockIdx.x * a.lay.slot, a.lay);
+    __shared__ SlotWs s_ws;
+    if (threadIdx.x == 0) s_ws = carve(a.ws + (size_t)blockIdx.x * a.lay.slot, a.lay);
+    __syncthreads();
+    const SlotWs& ws = s_ws;
     const int n_jobs = a.chain ? a.D : a.D * a.n_models;
     while (true) {
         __syncthreads();
