@@ -4,7 +4,7 @@
 // through generic pointers (the operands live in the per-slot HBM/L2 workspace; tiles are staged
 // through shared memory) and leaves the CTA synchronised on return.  Control flow is CTA-uniform.
 //
-// The work horse is cta_gemm: a 64x64x16-tiled, 4x4 register-blocked DFMA kernel with operand
+// The work horse is cta_gemm: a 64x64x16-tiled DMMA kernel fed by a cp.async panel ring, with operand
 // transposition, triangular operand masks (which also trim the k-range per tile) and a lower-only
 // output mode.  Cholesky, the triangular solves and the Cholesky reverse pass are blocked at 64 and
 // expressed through it; only the 64x64 diagonal blocks are factored / inverted in shared memory.
@@ -18,14 +18,18 @@
 #define GPC_BLK 64                 // block size of the blocked factorisations (= GEMM tile edge)
 #define GPC_BK 16                 // GEMM k-panel
 #define GPC_LDS 68                // padded leading dimension of the staged GEMM panels (== 4 mod 16: conflict-free DMMA fragments)
+#define GPC_LDR 20                // leading dimension of a row-major staged panel (64 rows x 16 k; == 4 mod 16 too)
+#define GPC_PANEL (64 * GPC_LDR)  // doubles per staged operand panel (>= GPC_BK * GPC_LDS)
+#ifndef GPC_STAGES
+#define GPC_STAGES 3              // depth of the cp.async panel ring
+#endif
 #define GPC_LDD 65                // padded leading dimension of the 64x64 diagonal block in smem
 
 enum { F_A_LOWER = 1, F_A_UPPER = 2, F_B_LOWER = 4, F_B_UPPER = 8, F_C_LOWER = 16 };
 
 // Shared-memory arena of the CTA (carved by the kernels in this library).
 struct CtaSmem {
-    double panelA[GPC_BK * GPC_LDS];
-    double panelB[GPC_BK * GPC_LDS];
+    double panel[GPC_STAGES][2][GPC_PANEL];   // cp.async ring of (A, B) k-panels
     double diag[GPC_BLK * GPC_LDD];      // diagonal block being factored / its inverse
     double red[64];                     // reduction scratch
     int flag;
@@ -82,9 +86,21 @@ __device__ __forceinline__ void dense_dmma884(double (&c)[2], double a, double b
                  : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-// Inner product of a 64 x 64 output tile on the FP64 tensor pipe: warp w owns rows 8w..8w+7 (eight 8 x 8 DMMA tiles);
-// the k-panels (16 deep) are staged k-major in shared memory and the global loads of the next panel are issued
-// before the current one is multiplied (register prefetch).
+// 8-byte asynchronous global -> shared copy; `ok == false` writes a zero without touching global memory.
+__device__ __forceinline__ void cp_async8(double* dst, const double* src, bool ok) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int nbytes = ok ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" :: "r"(d), "l"(src), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
+
+// Inner product of a 64 x 64 output tile on the FP64 tensor pipe: warp w owns rows 8w..8w+7 (eight 8 x 8 DMMA tiles).
+// The 16-deep k-panels travel global -> shared with cp.async through a GPC_STAGES-deep ring (the operands of the
+// dense path live in the slot's HBM workspace, far larger than L2 over all resident CTAs: two to three panels in
+// flight per CTA cover the DRAM latency); they land in their global layout (row tiles ld 20, k-major tiles ld 68,
+// both == 4 mod 16: conflict-free DMMA fragment loads), triangular masks and ragged edges are zero-filled by the copy.
 template <bool TA, bool TB>
 __device__ __noinline__ void cta_gemm(int m, int n, int k, double alpha, const double* __restrict__ A, int lda,
                          const double* __restrict__ B, int ldb, double beta, double* C, int ldc, int flags,
@@ -92,8 +108,14 @@ __device__ __noinline__ void cta_gemm(int m, int n, int k, double alpha, const d
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int ar = lane >> 2, ak = lane & 3;
-    double* As = sm->panelA;
-    double* Bs = sm->panelB;
+    // copy geometry: a row-major panel (64 x 16) gives thread t the element (t >> 4, t & 15) and every 16th row after
+    // it, a k-major panel (16 x 64) the element (t >> 6, t & 63) and every 4th k after it
+    constexpr int NE = (64 * GPC_BK) / GPC_THREADS;
+    const int a_i = TA ? (tid & 63) : (tid >> 4), a_k = TA ? (tid >> 6) : (tid & 15);
+    const int b_j = TB ? (tid >> 4) : (tid & 63), b_k = TB ? (tid & 15) : (tid >> 6);
+    const int a_dst = TA ? a_k * GPC_LDS + a_i : a_i * GPC_LDR + a_k;
+    const int b_dst = TB ? b_j * GPC_LDR + b_k : b_k * GPC_LDS + b_j;
+    const size_t a_step = TA ? (size_t)4 * lda : (size_t)16 * lda, b_step = TB ? (size_t)16 * ldb : (size_t)4 * ldb;
     for (int i0 = 0; i0 < m; i0 += 64) {
         for (int j0 = 0; j0 < n; j0 += 64) {
             if ((flags & F_C_LOWER) && j0 > i0 + 63) continue;
@@ -103,81 +125,69 @@ __device__ __noinline__ void cta_gemm(int m, int n, int k, double alpha, const d
             if (flags & F_A_LOWER) kmax = min(kmax, i0 + 64);
             if (flags & F_B_UPPER) kmax = min(kmax, j0 + 64);
             kmin &= ~(GPC_BK - 1);
+            const int npan = kmax > kmin ? (kmax - kmin + GPC_BK - 1) / GPC_BK : 0;
             double acc[8][2];
 #pragma unroll
             for (int t = 0; t < 8; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
-            double ra0, ra1, ra2, ra3, rb0, rb1, rb2, rb3;
             const bool warp_rows_valid = i0 + warp * 8 < m && (!(flags & F_C_LOWER) || j0 <= i0 + warp * 8 + 7);
             const int nct = min(8, (n - j0 + 7) >> 3);
-#define GPC_LOAD_A(dst, e, K0)                                                                         \
-            {                                                                                          \
-                const int idx = tid + (e) * GPC_THREADS;                                               \
-                int ii, kk;                                                                            \
-                if (!TA) { kk = idx & 15; ii = idx >> 4; } else { ii = idx & 63; kk = idx >> 6; }      \
-                const int gi = i0 + ii, gk = (K0) + kk;                                                \
-                double v = 0.0;                                                                        \
-                if (gi < m && gk < kmax) {                                                             \
-                    bool ok = true;                                                                    \
-                    if ((flags & F_A_LOWER) && gk > gi) ok = false;                                    \
-                    if ((flags & F_A_UPPER) && gk < gi) ok = false;                                    \
-                    if (ok) v = TA ? A[(size_t)gk * lda + gi] : A[(size_t)gi * lda + gk];              \
-                }                                                                                      \
-                dst = v;                                                                               \
-            }
-#define GPC_LOAD_B(dst, e, K0)                                                                         \
-            {                                                                                          \
-                const int idx = tid + (e) * GPC_THREADS;                                               \
-                int jj, kk;                                                                            \
-                if (!TB) { jj = idx & 63; kk = idx >> 6; } else { kk = idx & 15; jj = idx >> 4; }      \
-                const int gj = j0 + jj, gk = (K0) + kk;                                                \
-                double v = 0.0;                                                                        \
-                if (gj < n && gk < kmax) {                                                             \
-                    bool ok = true;                                                                    \
-                    if ((flags & F_B_LOWER) && gj > gk) ok = false;                                    \
-                    if ((flags & F_B_UPPER) && gj < gk) ok = false;                                    \
-                    if (ok) v = TB ? B[(size_t)gj * ldb + gk] : B[(size_t)gk * ldb + gj];              \
-                }                                                                                      \
-                dst = v;                                                                               \
-            }
-#define GPC_STORE_AB(e, va, vb)                                                                        \
-            {                                                                                          \
-                const int idx = tid + (e) * GPC_THREADS;                                               \
-                int ii, kk, jj, kb;                                                                    \
-                if (!TA) { kk = idx & 15; ii = idx >> 4; } else { ii = idx & 63; kk = idx >> 6; }      \
-                if (!TB) { jj = idx & 63; kb = idx >> 6; } else { kb = idx & 15; jj = idx >> 4; }      \
-                As[kk * GPC_LDS + ii] = va;                                                            \
-                Bs[kb * GPC_LDS + jj] = vb;                                                            \
-            }
-            if (kmin < kmax) {
-                GPC_LOAD_A(ra0, 0, kmin) GPC_LOAD_A(ra1, 1, kmin) GPC_LOAD_A(ra2, 2, kmin) GPC_LOAD_A(ra3, 3, kmin)
-                GPC_LOAD_B(rb0, 0, kmin) GPC_LOAD_B(rb1, 1, kmin) GPC_LOAD_B(rb2, 2, kmin) GPC_LOAD_B(rb3, 3, kmin)
-            }
-            for (int k0 = kmin; k0 < kmax; k0 += GPC_BK) {
-                GPC_STORE_AB(0, ra0, rb0) GPC_STORE_AB(1, ra1, rb1) GPC_STORE_AB(2, ra2, rb2) GPC_STORE_AB(3, ra3, rb3)
-                __syncthreads();
-                if (k0 + GPC_BK < kmax) {
-                    const int kn = k0 + GPC_BK;
-                    GPC_LOAD_A(ra0, 0, kn) GPC_LOAD_A(ra1, 1, kn) GPC_LOAD_A(ra2, 2, kn) GPC_LOAD_A(ra3, 3, kn)
-                    GPC_LOAD_B(rb0, 0, kn) GPC_LOAD_B(rb1, 1, kn) GPC_LOAD_B(rb2, 2, kn) GPC_LOAD_B(rb3, 3, kn)
+            // running source pointers of this thread's first element; element e sits a fixed stride further on
+            const double* pa = TA ? A + (size_t)(kmin + a_k) * lda + i0 + a_i : A + (size_t)(i0 + a_i) * lda + kmin + a_k;
+            const double* pb = TB ? B + (size_t)(j0 + b_j) * ldb + kmin + b_k : B + (size_t)(kmin + b_k) * ldb + j0 + b_j;
+            auto issue = [&](int pan) {
+                const int k0 = kmin + pan * GPC_BK;
+                double* As = sm->panel[pan % GPC_STAGES][0] + a_dst;
+                double* Bs = sm->panel[pan % GPC_STAGES][1] + b_dst;
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    {
+                        const int gi = i0 + a_i + (TA ? 0 : 16 * e), gk = k0 + a_k + (TA ? 4 * e : 0);
+                        bool ok = gi < m && gk < kmax;
+                        if ((flags & F_A_LOWER) && gk > gi) ok = false;
+                        if ((flags & F_A_UPPER) && gk < gi) ok = false;
+                        const double* src = pa + (size_t)e * a_step;
+                        cp_async8(As + e * (TA ? 4 * GPC_LDS : 16 * GPC_LDR), ok ? src : A, ok);
+                    }
+                    {
+                        const int gj = j0 + b_j + (TB ? 16 * e : 0), gk = k0 + b_k + (TB ? 0 : 4 * e);
+                        bool ok = gj < n && gk < kmax;
+                        if ((flags & F_B_LOWER) && gj > gk) ok = false;
+                        if ((flags & F_B_UPPER) && gj < gk) ok = false;
+                        const double* src = pb + (size_t)e * b_step;
+                        cp_async8(Bs + e * (TB ? 16 * GPC_LDR : 4 * GPC_LDS), ok ? src : B, ok);
+                    }
                 }
+                pa += TA ? (size_t)GPC_BK * lda : (size_t)GPC_BK;
+                pb += TB ? (size_t)GPC_BK : (size_t)GPC_BK * ldb;
+            };
+#pragma unroll
+            for (int s = 0; s < GPC_STAGES - 1; ++s) {
+                if (s < npan) issue(s);
+                cp_async_commit();
+            }
+            for (int pan = 0; pan < npan; ++pan) {
+                cp_async_wait<GPC_STAGES - 2>();   // this thread's share of panel `pan` has landed ...
+                __syncthreads();                   // ... and everyone's; everyone is also done with panel pan - 1
+                if (pan + GPC_STAGES - 1 < npan) issue(pan + GPC_STAGES - 1);   // refills the buffer of panel pan - 1
+                cp_async_commit();
                 if (warp_rows_valid) {             // ragged edge tiles: warps / column tiles beyond m, n do no math
+                    const double* As = sm->panel[pan % GPC_STAGES][0];
+                    const double* Bs = sm->panel[pan % GPC_STAGES][1];
 #pragma unroll
                     for (int kq = 0; kq < GPC_BK; kq += 4) {
-                        const double a = As[(kq + ak) * GPC_LDS + warp * 8 + ar];
+                        const double a = TA ? As[(kq + ak) * GPC_LDS + warp * 8 + ar] : As[(warp * 8 + ar) * GPC_LDR + kq + ak];
 #pragma unroll
                         for (int t = 0; t < 8; ++t) {
                             if (t < nct) {
-                                const double b = Bs[(kq + ak) * GPC_LDS + t * 8 + ar];
+                                const double b = TB ? Bs[(t * 8 + ar) * GPC_LDR + kq + ak] : Bs[(kq + ak) * GPC_LDS + t * 8 + ar];
                                 dense_dmma884(acc[t], a, b);
                             }
                         }
                     }
                 }
-                __syncthreads();
             }
-#undef GPC_LOAD_A
-#undef GPC_LOAD_B
-#undef GPC_STORE_AB
+            cp_async_wait<0>();
+            __syncthreads();       // all operand reads of this tile precede its stores (in-place use) and the next tile's copies
             const int gi = i0 + warp * 8 + ar;
             if (gi < m) {
 #pragma unroll

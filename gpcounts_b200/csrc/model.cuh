@@ -516,7 +516,7 @@ __device__ __forceinline__ bool use_fused(const ModelDev& md) {
     return md.kind == GPC_SVGP && md.M <= 64 && md.d <= 2 && md.kernel != GPC_BRANCH;
 }
 
-__device__ int model_eval(const ModelDev& md, const double* Z, const double* y, const double* scale,
+__device__ __noinline__ int model_eval_direct(const ModelDev& md, const double* Z, const double* y, const double* scale,
                           const double* theta, double* grad, double* f_out, const SlotWs& ws, CtaSmem* sm) {
 #ifdef GPC_FUSED_ONLY
     return eval_svgp_fused(md, Z, y, scale, theta, grad, f_out, ws, reinterpret_cast<FusedSmem*>(sm));
@@ -532,5 +532,23 @@ __device__ int model_eval(const ModelDev& md, const double* Z, const double* y, 
         case GPC_SGPR: return eval_sgpr(md, Z, y, theta, grad, f_out, ws, sm);
         default: return GPC_ST_CHOL;
     }
+#endif
+}
+
+// The optimiser calls the evaluator through a pointer: an indirect call is compiled to the plain ABI, so the register
+// allocation of the evaluators (cta_gemm above all) does not depend on how many values the calling kernel keeps live
+// across the call.  Called directly from k_fit, ptxas' interprocedural allocation left cta_gemm spilling inside its
+// panel loop under the 128-register cap of the dense instantiation (10 local loads per panel at L2 latency).
+typedef int (*ModelEvalFn)(const ModelDev&, const double*, const double*, const double*, const double*, double*, double*,
+                           const SlotWs&, CtaSmem*);
+__device__ ModelEvalFn g_model_eval = model_eval_direct;
+
+__device__ __forceinline__ int model_eval(const ModelDev& md, const double* Z, const double* y, const double* scale,
+                          const double* theta, double* grad, double* f_out, const SlotWs& ws, CtaSmem* sm) {
+#ifdef GPC_DENSE_ONLY
+    ModelEvalFn fn = *(volatile ModelEvalFn*)&g_model_eval;
+    return fn(md, Z, y, scale, theta, grad, f_out, ws, sm);
+#else
+    return model_eval_direct(md, Z, y, scale, theta, grad, f_out, ws, sm);
 #endif
 }
