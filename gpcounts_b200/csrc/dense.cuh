@@ -25,9 +25,17 @@
 #endif
 #define GPC_LDD 65                // padded leading dimension of the 64x64 diagonal block in smem
 
+// Visit every (i, j) of an R x C row-major array: warp w takes rows w, w + 8, ..., the lanes stride the columns
+// (coalesced); idx = i * C + j.  No integer division, unlike a flat index loop.
+#define GPC_FOR_2D(R, C, i, j)                                                  \
+    for (int i = threadIdx.x >> 5; i < (R); i += GPC_THREADS / 32)              \
+        for (int j = threadIdx.x & 31, idx = i * (C) + j; j < (C); j += 32, idx += 32)
+
 enum { F_A_LOWER = 1, F_A_UPPER = 2, F_B_LOWER = 4, F_B_UPPER = 8, F_C_LOWER = 16 };
 
-// Shared-memory arena of the CTA (carved by the kernels in this library).
+extern __shared__ __align__(16) unsigned char g_smem[];
+
+// Shared-memory arena of the CTA (carved by the kernels in this library at offset 0 of the dynamic shared memory).
 struct CtaSmem {
     double panel[GPC_STAGES][2][GPC_PANEL];   // cp.async ring of (A, B) k-panels
     double diag[GPC_BLK * GPC_LDD];      // diagonal block being factored / its inverse
@@ -105,6 +113,9 @@ template <bool TA, bool TB>
 __device__ __noinline__ void cta_gemm(int m, int n, int k, double alpha, const double* __restrict__ A, int lda,
                          const double* __restrict__ B, int ldb, double beta, double* C, int ldc, int flags,
                          CtaSmem* sm) {
+    // the arena sits at the start of the dynamic shared memory in every kernel of this library: address it through the
+    // shared window (no generic-pointer loads, and `sm`, which arrives on the stack, is never read here)
+    CtaSmem* ring = reinterpret_cast<CtaSmem*>(g_smem);
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int ar = lane >> 2, ak = lane & 3;
@@ -136,8 +147,8 @@ __device__ __noinline__ void cta_gemm(int m, int n, int k, double alpha, const d
             const double* pb = TB ? B + (size_t)(j0 + b_j) * ldb + kmin + b_k : B + (size_t)(kmin + b_k) * ldb + j0 + b_j;
             auto issue = [&](int pan) {
                 const int k0 = kmin + pan * GPC_BK;
-                double* As = sm->panel[pan % GPC_STAGES][0] + a_dst;
-                double* Bs = sm->panel[pan % GPC_STAGES][1] + b_dst;
+                double* As = ring->panel[pan % GPC_STAGES][0] + a_dst;
+                double* Bs = ring->panel[pan % GPC_STAGES][1] + b_dst;
 #pragma unroll
                 for (int e = 0; e < NE; ++e) {
                     {
@@ -171,8 +182,8 @@ __device__ __noinline__ void cta_gemm(int m, int n, int k, double alpha, const d
                 if (pan + GPC_STAGES - 1 < npan) issue(pan + GPC_STAGES - 1);   // refills the buffer of panel pan - 1
                 cp_async_commit();
                 if (warp_rows_valid) {             // ragged edge tiles: warps / column tiles beyond m, n do no math
-                    const double* As = sm->panel[pan % GPC_STAGES][0];
-                    const double* Bs = sm->panel[pan % GPC_STAGES][1];
+                    const double* As = ring->panel[pan % GPC_STAGES][0];
+                    const double* Bs = ring->panel[pan % GPC_STAGES][1];
 #pragma unroll
                     for (int kq = 0; kq < GPC_BK; kq += 4) {
                         const double a = TA ? As[(kq + ak) * GPC_LDS + warp * 8 + ar] : As[(warp * 8 + ar) * GPC_LDR + kq + ak];
@@ -186,9 +197,20 @@ __device__ __noinline__ void cta_gemm(int m, int n, int k, double alpha, const d
                     }
                 }
             }
+            // the old C values (beta != 0) are fetched while the last DMMAs drain, ahead of the barrier
+            const int gi = i0 + warp * 8 + ar;
+            double cold[8][2];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int gj = j0 + t * 8 + 2 * ak + c;
+                    const bool live = gi < m && gj < n && !((flags & F_C_LOWER) && gj > gi);
+                    cold[t][c] = (beta != 0.0 && live) ? C[(size_t)gi * ldc + gj] : 0.0;
+                }
+            }
             cp_async_wait<0>();
             __syncthreads();       // all operand reads of this tile precede its stores (in-place use) and the next tile's copies
-            const int gi = i0 + warp * 8 + ar;
             if (gi < m) {
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
@@ -197,10 +219,7 @@ __device__ __noinline__ void cta_gemm(int m, int n, int k, double alpha, const d
                         const int gj = j0 + t * 8 + 2 * ak + c;
                         if (gj >= n) continue;
                         if ((flags & F_C_LOWER) && gj > gi) continue;
-                        double* p = C + (size_t)gi * ldc + gj;
-                        double v = alpha * acc[t][c];
-                        if (beta != 0.0) v += beta * (*p);
-                        *p = v;
+                        C[(size_t)gi * ldc + gj] = fma(beta, cold[t][c], alpha * acc[t][c]);
                     }
                 }
             }
@@ -212,25 +231,48 @@ __device__ __noinline__ void cta_gemm(int m, int n, int k, double alpha, const d
 // Factor the nb x nb (nb <= 64) SPD block held in sm->diag (lower part used) in place: diag = chol.
 // Returns false (CTA-uniform) on a non-positive or NaN pivot.
 __device__ bool smem_chol(CtaSmem* sm, int nb) {
+    // Left-looking, four lanes per row: lane q of row i keeps l_ik, k = q (mod 4), in registers; an element is one dot
+    // product and every row group recomputes the pivot from row j in shared memory: ONE barrier per column.
     double* D = sm->diag;
     const int tid = threadIdx.x;
+    const int i = tid >> 2, q = tid & 3;
+    double lk[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) lk[t] = 0.0;
+    bool ok = true;
+    double lii = 0.0;
     for (int j = 0; j < nb; ++j) {
         __syncthreads();
-        const double djj = D[j * GPC_LDD + j];
-        if (!(djj > 0.0)) return false;           // NaN or non-positive pivot (uniform: all read the same value)
-        const double r = sqrt(djj);
-        __syncthreads();
-        if (tid == j) D[j * GPC_LDD + j] = r;
-        if (tid > j && tid < nb) D[tid * GPC_LDD + j] /= r;
-        __syncthreads();
-        const int rem = nb - j - 1;
-        for (int idx = tid; idx < rem * rem; idx += GPC_THREADS) {
-            const int i = j + 1 + idx / rem, c = j + 1 + idx % rem;
-            if (c <= i) D[i * GPC_LDD + c] = fma(-D[i * GPC_LDD + j], D[c * GPC_LDD + j], D[i * GPC_LDD + c]);
+        double pj = 0.0, pi = 0.0;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int k = q + 4 * t;
+            if (k < j) {
+                const double ljk = D[j * GPC_LDD + k];
+                pj = fma(ljk, ljk, pj);
+                pi = fma(lk[t], ljk, pi);
+            }
+        }
+        pj += __shfl_xor_sync(0xffffffffu, pj, 1); pj += __shfl_xor_sync(0xffffffffu, pj, 2);
+        pi += __shfl_xor_sync(0xffffffffu, pi, 1); pi += __shfl_xor_sync(0xffffffffu, pi, 2);
+        const double djj = D[j * GPC_LDD + j] - pj;
+        if (!(djj > 0.0)) { ok = false; break; }   // NaN or non-positive pivot (uniform: every thread sees the same value)
+        const double ljj = sqrt(djj);
+        if (i < nb && i >= j) {
+            const double lij = (i == j) ? ljj : (D[i * GPC_LDD + j] - pi) / ljj;
+#pragma unroll
+            for (int t = 0; t < 16; ++t)
+                if (q + 4 * t == j) lk[t] = lij;
+            // the diagonal entry still holds a_jj, which slower warps read for this column's pivot: it is replaced
+            // by l_jj only after the loop
+            if (i == j) lii = lij;
+            else if (q == 0) D[i * GPC_LDD + j] = lij;
         }
     }
     __syncthreads();
-    return true;
+    if (ok && q == 0 && i < nb) D[i * GPC_LDD + i] = lii;
+    __syncthreads();
+    return ok;
 }
 
 // inv (global, nb x nb row-major, ld = GPC_BLK) <- inverse of the lower-triangular block in sm->diag.
@@ -273,13 +315,11 @@ __device__ bool cta_potrf(int n, double* A, int lda, double* dinv, CtaSmem* sm) 
             cta_gemm<false, true>(n - j0, jb, j0, -1.0, A + (size_t)j0 * lda, lda, A + (size_t)j0 * lda, lda, 1.0,
                                   A + (size_t)j0 * lda + j0, lda, 0, sm);
         // diagonal block -> smem, factor, write back, invert
-        for (int idx = tid; idx < jb * jb; idx += GPC_THREADS) {
-            const int i = idx / jb, c = idx % jb;
+        GPC_FOR_2D(jb, jb, i, c) {
             sm->diag[i * GPC_LDD + c] = (c <= i) ? A[(size_t)(j0 + i) * lda + j0 + c] : 0.0;
         }
         if (!smem_chol(sm, jb)) return false;
-        for (int idx = tid; idx < jb * jb; idx += GPC_THREADS) {
-            const int i = idx / jb, c = idx % jb;
+        GPC_FOR_2D(jb, jb, i, c) {
             if (c <= i) A[(size_t)(j0 + i) * lda + j0 + c] = sm->diag[i * GPC_LDD + c];
         }
         double* inv = dinv + (size_t)blk * GPC_BLK * GPC_BLK;
@@ -342,8 +382,7 @@ __device__ void cta_chol_backward(int n, const double* L, int ldl, const double*
                                   int ldt, CtaSmem* sm) {
     // T = tril(L^T * Lbar)
     cta_gemm<true, false>(n, n, n, 1.0, L, ldl, G, ldg, 0.0, T, ldt, F_A_UPPER | F_B_LOWER | F_C_LOWER, sm);
-    for (int idx = threadIdx.x; idx < n * n; idx += GPC_THREADS) {
-        const int i = idx / n, j = idx % n;
+    GPC_FOR_2D(n, n, i, j) {
         const double v = T[(size_t)i * ldt + j];
         G[(size_t)i * ldg + j] = (j < i) ? v : (j == i ? 0.5 * v : 0.0);
     }

@@ -111,7 +111,6 @@ struct FitArgs {
     int trace_cap, trace_gene, trace_model;
 };
 
-extern __shared__ __align__(16) unsigned char g_smem[];
 
 // The dense (CtaSmem) and fused (FusedSmem) evaluators overlay the same shared-memory region.
 #ifndef GPC_MIN_BLOCKS

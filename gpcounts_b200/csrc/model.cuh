@@ -114,8 +114,7 @@ __device__ __forceinline__ void store_hyper_grad(const ModelDev& md, const Hyper
 
 // K0 (n x n, full symmetric, no jitter) and L = K0 + shift*I from inputs Xs (n x d).
 __device__ void build_gram_square(const KernParams& kp, int n, const double* Xs, double shift, double* K0, double* L) {
-    for (int idx = threadIdx.x; idx < n * n; idx += GPC_THREADS) {
-        const int i = idx / n, j = idx % n;
+    GPC_FOR_2D(n, n, i, j) {
         bool cross;
         const double r2 = kern_r2(kp, Xs + (size_t)i * kp.d, Xs + (size_t)j * kp.d, cross);
         const double k = kern_val(kp, r2, cross);
@@ -129,8 +128,7 @@ __device__ void build_gram_square(const KernParams& kp, int n, const double* Xs,
 __device__ void gram_square_grad(const KernParams& kp, int n, const double* Xs, const double* K0, const double* G,
                                  double& dvar, double& dls, CtaSmem* sm) {
     double acc[2] = {0.0, 0.0};
-    for (int idx = threadIdx.x; idx < n * n; idx += GPC_THREADS) {
-        const int i = idx / n, j = idx % n;
+    GPC_FOR_2D(n, n, i, j) {
         bool cross;
         const double r2 = kern_r2(kp, Xs + (size_t)i * kp.d, Xs + (size_t)j * kp.d, cross);
         kern_grad_acc(kp, G[idx], K0[idx], r2, cross, acc[0], acc[1]);
@@ -144,8 +142,7 @@ __device__ __forceinline__ size_t tri_index(int i, int j) { return (size_t)i * (
 
 // Unpack tril(q_sqrt) (row-major packed) into a full Mv x Mv matrix with a zero upper triangle.
 __device__ void unpack_lq(int mv, const double* packed, double* Lq) {
-    for (int idx = threadIdx.x; idx < mv * mv; idx += GPC_THREADS) {
-        const int i = idx / mv, j = idx % mv;
+    GPC_FOR_2D(mv, mv, i, j) {
         Lq[idx] = (j <= i) ? packed[tri_index(i, j)] : 0.0;
     }
     __syncthreads();
@@ -218,22 +215,19 @@ __device__ __noinline__ int eval_vgp(const ModelDev& md, const double* y, const 
     double ve, dalpha, dkm;
     lik_pass(md, h, N, fmean, fvar, y, scale, gm, gv, ve, dalpha, dkm, sm);
     // Cbar = 2 diag(gv) C
-    for (int idx = tid; idx < N * N; idx += GPC_THREADS) {
-        const int i = idx / N, j = idx % N;
+    GPC_FOR_2D(N, N, i, j) {
         if (j <= i) ws.G1[idx] *= 2.0 * gv[i];
     }
     __syncthreads();
     // Lbar = tril(Cbar Lq^T + gm q_mu^T)
     cta_gemm<false, true>(N, N, N, 1.0, ws.G1, N, ws.Lq, N, 0.0, ws.G2, N, F_A_LOWER | F_B_UPPER | F_C_LOWER, sm);
-    for (int idx = tid; idx < N * N; idx += GPC_THREADS) {
-        const int i = idx / N, j = idx % N;
+    GPC_FOR_2D(N, N, i, j) {
         if (j <= i) ws.G2[idx] = fma(gm[i], q_mu[j], ws.G2[idx]);
     }
     // grad Lq = tril(L^T Cbar) - (Lq - diag(1/Lq_ii))
     cta_gemm<true, false>(N, N, N, 1.0, ws.L, N, ws.G1, N, 0.0, ws.G3, N, F_A_UPPER | F_B_LOWER | F_C_LOWER, sm);
     double* glq = grad + GPC_NHYP + N;
-    for (int idx = tid; idx < N * N; idx += GPC_THREADS) {
-        const int i = idx / N, j = idx % N;
+    GPC_FOR_2D(N, N, i, j) {
         if (j <= i) {
             const double l = ws.Lq[idx];
             glq[tri_index(i, j)] = ws.G3[idx] - (i == j ? l - 1.0 / l : l);
@@ -274,8 +268,7 @@ __device__ __noinline__ int eval_svgp(const ModelDev& md, const double* Z, const
     const double kdiag = h.var + (md.kernel == GPC_BRANCH ? GPC_BRANCH_NOISE : 0.0);
     build_gram_square(kp, M, Z, shift, ws.K0, ws.L);
     // Kuf and A (= copy of Kuf, solved in place)
-    for (int idx = tid; idx < M * N; idx += GPC_THREADS) {
-        const int i = idx / N, n = idx % N;
+    GPC_FOR_2D(M, N, i, n) {
         bool cross;
         const double r2 = kern_r2(kp, Z + (size_t)i * kp.d, md.X + (size_t)n * kp.d, cross);
         const double k = kern_val(kp, r2, cross);
@@ -305,8 +298,7 @@ __device__ __noinline__ int eval_svgp(const ModelDev& md, const double* Z, const
     double gv_sum = 0.0;
     for (int n = tid; n < N; n += GPC_THREADS) gv_sum += gv[n];
     gv_sum = cta_sum(gv_sum, sm->red);
-    for (int idx = tid; idx < M * N; idx += GPC_THREADS) {
-        const int i = idx / N, n = idx % N;
+    GPC_FOR_2D(M, N, i, n) {
         const double g2 = 2.0 * gv[n];
         ws.B[idx] *= g2;
         ws.S[idx] = fma(q_mu[i], gm[n], -g2 * ws.A[idx]);
@@ -323,8 +315,7 @@ __device__ __noinline__ int eval_svgp(const ModelDev& md, const double* Z, const
     // grad Lq = tril(A Bbar^T) - (Lq - diag(1/Lq_ii))
     cta_gemm<false, true>(M, M, N, 1.0, ws.A, N, ws.B, N, 0.0, ws.G1, M, F_C_LOWER, sm);
     double* glq = grad + GPC_NHYP + M;
-    for (int idx = tid; idx < M * M; idx += GPC_THREADS) {
-        const int i = idx / M, j = idx % M;
+    GPC_FOR_2D(M, M, i, j) {
         if (j <= i) {
             const double l = ws.Lq[idx];
             glq[tri_index(i, j)] = ws.G1[idx] - (i == j ? l - 1.0 / l : l);
@@ -339,8 +330,7 @@ __device__ __noinline__ int eval_svgp(const ModelDev& md, const double* Z, const
         // Lm bar = -tril(S A^T)
         cta_gemm<false, true>(M, M, N, -1.0, ws.S, N, ws.A, N, 0.0, ws.G2, M, F_C_LOWER, sm);
         double acc[2] = {0.0, 0.0};
-        for (int idx = tid; idx < M * N; idx += GPC_THREADS) {
-            const int i = idx / N, n = idx % N;
+        GPC_FOR_2D(M, N, i, n) {
             bool cross;
             const double r2 = kern_r2(kp, Z + (size_t)i * kp.d, md.X + (size_t)n * kp.d, cross);
             kern_grad_acc(kp, ws.S[idx], ws.Kuf[idx], r2, cross, acc[0], acc[1]);
@@ -382,8 +372,7 @@ __device__ __noinline__ int eval_gpr(const ModelDev& md, const double* y, const 
     cta_sum_n<2>(acc, sm->red);
     cta_trsm_left_t(N, 1, ws.L, N, ws.dinv, w, 1, sm);
     // Lbar = tril(w v^T) - diag(1/L_ii)
-    for (int idx = tid; idx < N * N; idx += GPC_THREADS) {
-        const int i = idx / N, j = idx % N;
+    GPC_FOR_2D(N, N, i, j) {
         if (j <= i) ws.G2[idx] = w[i] * v[j] - (i == j ? 1.0 / ws.L[idx] : 0.0);
     }
     __syncthreads();
@@ -417,8 +406,7 @@ __device__ __noinline__ int eval_sgpr(const ModelDev& md, const double* Z, const
     double* V = ws.A; double* Vb = ws.B; double* Bm = ws.Lq; double* VVt = ws.G4;
     double* cvec = ws.v0; double* wvec = ws.v1; double* uvec = ws.v2;
     build_gram_square(kp, M, Z, shift, ws.K0, ws.L);
-    for (int idx = tid; idx < M * N; idx += GPC_THREADS) {
-        const int i = idx / N, n = idx % N;
+    GPC_FOR_2D(M, N, i, n) {
         bool cross;
         const double r2 = kern_r2(kp, Z + (size_t)i * kp.d, md.X + (size_t)n * kp.d, cross);
         const double k = kern_val(kp, r2, cross);
@@ -431,8 +419,7 @@ __device__ __noinline__ int eval_sgpr(const ModelDev& md, const double* Z, const
     // VVt = V V^T / s2 (full), B = VVt + I
     cta_gemm<false, true>(M, M, N, is2, V, N, V, N, 0.0, VVt, M, 0, sm);
     double acc[2] = {0.0, 0.0};
-    for (int idx = tid; idx < M * M; idx += GPC_THREADS) {
-        const int i = idx / M, j = idx % M;
+    GPC_FOR_2D(M, M, i, j) {
         const double v = VVt[idx];
         Bm[idx] = (i == j) ? v + 1.0 : v;
         if (i == j) acc[0] += v;                       // tr(V V^T) / s2
@@ -460,16 +447,14 @@ __device__ __noinline__ int eval_sgpr(const ModelDev& md, const double* Z, const
     const double cc = a3[0], logdetLB = a3[1];
     cta_trsm_left_t(M, 1, Bm, M, ws.dinv2, wvec, 1, sm);
     // LB-bar = -tril(w c^T) - diag(1 / LB_ii)  -> G2;  reverse pass of chol(B)
-    for (int idx = tid; idx < M * M; idx += GPC_THREADS) {
-        const int i = idx / M, j = idx % M;
+    GPC_FOR_2D(M, M, i, j) {
         if (j <= i) ws.G2[idx] = -wvec[i] * cvec[j] - (i == j ? 1.0 / Bm[idx] : 0.0);
     }
     __syncthreads();
     cta_chol_backward(M, Bm, M, ws.dinv2, ws.G2, M, ws.G3, M, sm);
     // W = Bbar + Bbar^T -> G1;  <Bbar, VVt>;  w . a
     double a2[2] = {0.0, 0.0};
-    for (int idx = tid; idx < M * M; idx += GPC_THREADS) {
-        const int i = idx / M, j = idx % M;
+    GPC_FOR_2D(M, M, i, j) {
         ws.G1[idx] = ws.G2[idx] + ws.G2[(size_t)j * M + i];
         a2[0] = fma(ws.G2[idx], VVt[idx], a2[0]);
     }
@@ -477,16 +462,14 @@ __device__ __noinline__ int eval_sgpr(const ModelDev& md, const double* Z, const
     cta_sum_n<2>(a2, sm->red);
     // Vbar = (W V + w y^T + V) / s2
     cta_gemm<false, false>(M, N, M, is2, ws.G1, M, V, N, 0.0, Vb, N, 0, sm);
-    for (int idx = tid; idx < M * N; idx += GPC_THREADS) {
-        const int i = idx / N, n = idx % N;
+    GPC_FOR_2D(M, N, i, n) {
         Vb[idx] += (wvec[i] * y[n] + V[idx]) * is2;
     }
     __syncthreads();
     cta_trsm_left_t(M, N, ws.L, M, ws.dinv, Vb, N, sm);                         // S = L^-T Vbar = Kuf-bar
     cta_gemm<false, true>(M, M, N, -1.0, Vb, N, V, N, 0.0, ws.G2, M, F_C_LOWER, sm);   // L-bar = -tril(S V^T)
     double ak[2] = {0.0, 0.0};
-    for (int idx = tid; idx < M * N; idx += GPC_THREADS) {
-        const int i = idx / N, n = idx % N;
+    GPC_FOR_2D(M, N, i, n) {
         bool cross;
         const double r2 = kern_r2(kp, Z + (size_t)i * kp.d, md.X + (size_t)n * kp.d, cross);
         kern_grad_acc(kp, Vb[idx], ws.Kuf[idx], r2, cross, ak[0], ak[1]);
@@ -539,9 +522,11 @@ __device__ __noinline__ int model_eval_direct(const ModelDev& md, const double* 
 // allocation of the evaluators (cta_gemm above all) does not depend on how many values the calling kernel keeps live
 // across the call.  Called directly from k_fit, ptxas' interprocedural allocation left cta_gemm spilling inside its
 // panel loop under the 128-register cap of the dense instantiation (10 local loads per panel at L2 latency).
+#ifdef GPC_DENSE_ONLY
 typedef int (*ModelEvalFn)(const ModelDev&, const double*, const double*, const double*, const double*, double*, double*,
                            const SlotWs&, CtaSmem*);
 __device__ ModelEvalFn g_model_eval = model_eval_direct;
+#endif
 
 __device__ __forceinline__ int model_eval(const ModelDev& md, const double* Z, const double* y, const double* scale,
                           const double* theta, double* grad, double* f_out, const SlotWs& ws, CtaSmem* sm) {

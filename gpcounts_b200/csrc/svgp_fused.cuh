@@ -143,6 +143,7 @@ __device__ bool fz_chol(double* D, int n) {
 #pragma unroll
     for (int t = 0; t < 16; ++t) lk[t] = 0.0;
     bool ok = true;
+    double lii = 0.0;
     for (int j = 0; j < n; ++j) {
         __syncthreads();
         // partial sums over k = q, q+4, ... < j of l_jk^2 (pivot) and l_ik l_jk (this row)
@@ -166,9 +167,14 @@ __device__ bool fz_chol(double* D, int n) {
 #pragma unroll
             for (int t = 0; t < 16; ++t)
                 if (q + 4 * t == j) lk[t] = lij;
-            if (q == 0) D[i * FZ_LD + j] = lij;    // column j of row i is final
+            // the diagonal entry still holds a_jj, which slower warps read for this column's pivot: it is replaced
+            // by l_jj only after the loop
+            if (i == j) lii = lij;
+            else if (q == 0) D[i * FZ_LD + j] = lij;    // column j of row i is final
         }
     }
+    __syncthreads();
+    if (ok && q == 0 && i < n) D[i * FZ_LD + i] = lii;
     __syncthreads();
     return ok;
 }
