@@ -335,6 +335,18 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
     const int rA = pr * 8, rB = (nrb - 1 - pr) * 8;
     const int ctA = hw * FZ_TPH, ctB = 4 + hw * FZ_TPH;
     double sum_ve = 0.0, sum_da = 0.0, sum_dk = 0.0, sum_gv = 0.0, sum_sk = 0.0, sum_skr = 0.0;
+    // node-independent likelihood terms (lgamma / digamma of k + y) of all N points in one converged pass: inside the
+    // tile loop they would run on 8 of a warp's 32 lanes, three serialised special-function calls per tile
+    if (md.lik == GPC_NB || md.lik == GPC_ZINB) {
+        const double k2 = lp.k * lp.k;
+        for (int n = tid; n < N; n += GPC_THREADS) {
+            const double yy = y[n];
+            if (md.lik == GPC_NB || yy != 0.0) {
+                sum_ve += (lgamma(lp.k + yy) - lp.lgamma_k) - lgamma(yy + 1.0);
+                sum_da += -k2 * (digamma_pos(lp.k + yy) - lp.digamma_k);
+            }
+        }
+    }
     const int ar = lane >> 2, ac = 2 * (lane & 3);
     for (int n0 = 0; n0 < N; n0 += 64) {
         const int nt = min(64, N - n0);
@@ -427,11 +439,6 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
                     const double sd = sqrt(fv);
                     const LikPart o = lik_nodes<FZ_LPC>(lp, fm, sd, yy, log(fs->col[5][c]), part);
                     ve = o.ve; gm = o.gm; gz = o.gz; da = o.da; dk = o.dk; poison = o.poison;
-                    // the node-independent lgamma / digamma terms go to the lanes with the fewest nodes
-                    const bool has_const = (md.lik == GPC_NB) || (yy != 0.0);
-                    if (part == FZ_LPC - 3 && has_const) ve += lgamma(lp.k + yy) - lp.lgamma_k;
-                    if (part == FZ_LPC - 1 && has_const) ve -= lgamma(yy + 1.0);
-                    if (part == FZ_LPC - 2 && has_const) da += -(lp.k * lp.k) * (digamma_pos(lp.k + yy) - lp.digamma_k);
                 }
             }
             if (poison) { gm = NAN; gz = NAN; dk = NAN; }
