@@ -243,16 +243,17 @@ __device__ bool smem_chol(CtaSmem* sm, int nb) {
     double lii = 0.0;
     for (int j = 0; j < nb; ++j) {
         __syncthreads();
-        double pj = 0.0, pi = 0.0;
+        double pj4[4] = {0.0, 0.0, 0.0, 0.0}, pi4[4] = {0.0, 0.0, 0.0, 0.0};   // 4-deep instead of 16-deep FMA chains
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
             const int k = q + 4 * t;
             if (k < j) {
                 const double ljk = D[j * GPC_LDD + k];
-                pj = fma(ljk, ljk, pj);
-                pi = fma(lk[t], ljk, pi);
+                pj4[t & 3] = fma(ljk, ljk, pj4[t & 3]);
+                pi4[t & 3] = fma(lk[t], ljk, pi4[t & 3]);
             }
         }
+        double pj = (pj4[0] + pj4[1]) + (pj4[2] + pj4[3]), pi = (pi4[0] + pi4[1]) + (pi4[2] + pi4[3]);
         pj += __shfl_xor_sync(0xffffffffu, pj, 1); pj += __shfl_xor_sync(0xffffffffu, pj, 2);
         pi += __shfl_xor_sync(0xffffffffu, pi, 1); pi += __shfl_xor_sync(0xffffffffu, pi, 2);
         const double djj = D[j * GPC_LDD + j] - pj;
@@ -286,12 +287,13 @@ __device__ void smem_tri_inverse(CtaSmem* sm, int nb, double* inv) {
 #pragma unroll
     for (int t = 0; t < 16; ++t) xk[t] = 0.0;
     for (int i = 0; i < nb; ++i) {
-        double part = 0.0;
+        double p4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
             const int kk = q + 4 * t;
-            if (kk < i) part = fma(D[i * GPC_LDD + kk], xk[t], part);
+            if (kk < i) p4[t & 3] = fma(D[i * GPC_LDD + kk], xk[t], p4[t & 3]);
         }
+        double part = (p4[0] + p4[1]) + (p4[2] + p4[3]);
         part += __shfl_xor_sync(0xffffffffu, part, 1);
         part += __shfl_xor_sync(0xffffffffu, part, 2);
         const double xi = (c < nb && i >= c) ? ((i == c ? 1.0 : 0.0) - part) / D[i * GPC_LDD + i] : 0.0;

@@ -147,16 +147,18 @@ __device__ bool fz_chol(double* D, int n) {
     for (int j = 0; j < n; ++j) {
         __syncthreads();
         // partial sums over k = q, q+4, ... < j of l_jk^2 (pivot) and l_ik l_jk (this row)
-        double pj = 0.0, pi = 0.0;
+        // four interleaved partial sums per dot product: the dependent FMA chain is 4 deep instead of 16
+        double pj4[4] = {0.0, 0.0, 0.0, 0.0}, pi4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
             const int k = q + 4 * t;
             if (k < j) {
                 const double ljk = D[j * FZ_LD + k];
-                pj = fma(ljk, ljk, pj);
-                pi = fma(lk[t], ljk, pi);
+                pj4[t & 3] = fma(ljk, ljk, pj4[t & 3]);
+                pi4[t & 3] = fma(lk[t], ljk, pi4[t & 3]);
             }
         }
+        double pj = (pj4[0] + pj4[1]) + (pj4[2] + pj4[3]), pi = (pi4[0] + pi4[1]) + (pi4[2] + pi4[3]);
         pj += __shfl_xor_sync(0xffffffffu, pj, 1); pj += __shfl_xor_sync(0xffffffffu, pj, 2);
         pi += __shfl_xor_sync(0xffffffffu, pi, 1); pi += __shfl_xor_sync(0xffffffffu, pi, 2);
         const double djj = D[j * FZ_LD + j] - pj;
@@ -189,12 +191,13 @@ __device__ void fz_tri_inverse(const double* L, int n, double* X) {
     for (int i = 0; i < 64; ++i) {
         double xi;
         if (i < n) {
-            double part = 0.0;
+            double p4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
             for (int t = 0; t < 16; ++t) {
                 const int kk = q + 4 * t;
-                if (kk < i) part = fma(L[i * FZ_LD + kk], xk[t], part);
+                if (kk < i) p4[t & 3] = fma(L[i * FZ_LD + kk], xk[t], p4[t & 3]);
             }
+            double part = (p4[0] + p4[1]) + (p4[2] + p4[3]);
             part += __shfl_xor_sync(0xffffffffu, part, 1);
             part += __shfl_xor_sync(0xffffffffu, part, 2);
             xi = (c < n && i >= c) ? ((i == c ? 1.0 : 0.0) - part) / L[i * FZ_LD + i] : 0.0;
