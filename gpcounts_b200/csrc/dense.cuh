@@ -35,6 +35,8 @@ enum { F_A_LOWER = 1, F_A_UPPER = 2, F_B_LOWER = 4, F_B_UPPER = 8, F_C_LOWER = 1
 
 extern __shared__ __align__(16) unsigned char g_smem[];
 
+__device__ __forceinline__ struct CtaSmem* cta_arena();
+
 // Shared-memory arena of the CTA (carved by the kernels in this library at offset 0 of the dynamic shared memory).
 struct CtaSmem {
     double panel[GPC_STAGES][2][GPC_PANEL];   // cp.async ring of (A, B) k-panels
@@ -42,6 +44,10 @@ struct CtaSmem {
     double red[64];                     // reduction scratch
     int flag;
 };
+
+// The arena through the shared window (see model.cuh: evaluators are reached through a function pointer, so a
+// `CtaSmem*` argument is a generic pointer to the compiler; this one is known to be shared memory).
+__device__ __forceinline__ CtaSmem* cta_arena() { return reinterpret_cast<CtaSmem*>(g_smem); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -113,6 +119,7 @@ template <bool TA, bool TB>
 __device__ __noinline__ void cta_gemm(int m, int n, int k, double alpha, const double* __restrict__ A, int lda,
                          const double* __restrict__ B, int ldb, double beta, double* C, int ldc, int flags,
                          CtaSmem* sm) {
+    sm = cta_arena();
     // the arena sits at the start of the dynamic shared memory in every kernel of this library: address it through the
     // shared window (no generic-pointer loads, and `sm`, which arrives on the stack, is never read here)
     CtaSmem* ring = reinterpret_cast<CtaSmem*>(g_smem);
@@ -231,6 +238,7 @@ __device__ __noinline__ void cta_gemm(int m, int n, int k, double alpha, const d
 // Factor the nb x nb (nb <= 64) SPD block held in sm->diag (lower part used) in place: diag = chol.
 // Returns false (CTA-uniform) on a non-positive or NaN pivot.
 __device__ bool smem_chol(CtaSmem* sm, int nb) {
+    sm = cta_arena();
     // Left-looking, four lanes per row: lane q of row i keeps l_ik, k = q (mod 4), in registers; an element is one dot
     // product and every row group recomputes the pivot from row j in shared memory: ONE barrier per column.
     double* D = sm->diag;
@@ -279,6 +287,7 @@ __device__ bool smem_chol(CtaSmem* sm, int nb) {
 // inv (global, nb x nb row-major, ld = GPC_BLK) <- inverse of the lower-triangular block in sm->diag.
 // Four threads per column split the substitution dot products.
 __device__ void smem_tri_inverse(CtaSmem* sm, int nb, double* inv) {
+    sm = cta_arena();
     const double* D = sm->diag;
     const int tid = threadIdx.x;
     const int c = tid >> 2, q = tid & 3;
@@ -309,6 +318,7 @@ __device__ void smem_tri_inverse(CtaSmem* sm, int nb, double* inv) {
 // dinv receives the inverses of the 64x64 diagonal blocks of L (ceil(n/64) blocks of GPC_BLK*GPC_BLK doubles).
 // Returns false on failure (CTA-uniform).
 __device__ bool cta_potrf(int n, double* A, int lda, double* dinv, CtaSmem* sm) {
+    sm = cta_arena();
     const int tid = threadIdx.x;
     for (int j0 = 0, blk = 0; j0 < n; j0 += GPC_BLK, ++blk) {
         const int jb = min(GPC_BLK, n - j0);
@@ -338,6 +348,7 @@ __device__ bool cta_potrf(int n, double* A, int lda, double* dinv, CtaSmem* sm) 
 // B (n x nrhs) <- L^-1 B
 __device__ void cta_trsm_left(int n, int nrhs, const double* L, int ldl, const double* dinv, double* B, int ldb,
                               CtaSmem* sm) {
+    sm = cta_arena();
     for (int i0 = 0, blk = 0; i0 < n; i0 += GPC_BLK, ++blk) {
         const int ib = min(GPC_BLK, n - i0);
         if (i0 > 0)
@@ -351,6 +362,7 @@ __device__ void cta_trsm_left(int n, int nrhs, const double* L, int ldl, const d
 // B (n x nrhs) <- L^-T B
 __device__ void cta_trsm_left_t(int n, int nrhs, const double* L, int ldl, const double* dinv, double* B, int ldb,
                                 CtaSmem* sm) {
+    sm = cta_arena();
     const int nblk = (n + GPC_BLK - 1) / GPC_BLK;
     for (int blk = nblk - 1; blk >= 0; --blk) {
         const int i0 = blk * GPC_BLK, ib = min(GPC_BLK, n - i0), i1 = i0 + ib;
@@ -365,6 +377,7 @@ __device__ void cta_trsm_left_t(int n, int nrhs, const double* L, int ldl, const
 // B (mrows x n) <- B L^-1
 __device__ void cta_trsm_right(int mrows, int n, const double* L, int ldl, const double* dinv, double* B, int ldb,
                                CtaSmem* sm) {
+    sm = cta_arena();
     const int nblk = (n + GPC_BLK - 1) / GPC_BLK;
     for (int blk = nblk - 1; blk >= 0; --blk) {
         const int j0 = blk * GPC_BLK, jb = min(GPC_BLK, n - j0), j1 = j0 + jb;
@@ -382,6 +395,7 @@ __device__ void cta_trsm_right(int mrows, int n, const double* L, int ldl, const
 // T is an n x n scratch matrix.
 __device__ void cta_chol_backward(int n, const double* L, int ldl, const double* dinv, double* G, int ldg, double* T,
                                   int ldt, CtaSmem* sm) {
+    sm = cta_arena();
     // T = tril(L^T * Lbar)
     cta_gemm<true, false>(n, n, n, 1.0, L, ldl, G, ldg, 0.0, T, ldt, F_A_UPPER | F_B_LOWER | F_C_LOWER, sm);
     GPC_FOR_2D(n, n, i, j) {

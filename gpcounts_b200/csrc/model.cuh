@@ -127,6 +127,7 @@ __device__ void build_gram_square(const KernParams& kp, int n, const double* Xs,
 // <G, dK/dvar>, <G, dK/dls> over the full n x n matrix G against the stored Gram K0.
 __device__ void gram_square_grad(const KernParams& kp, int n, const double* Xs, const double* K0, const double* G,
                                  double& dvar, double& dls, CtaSmem* sm) {
+    sm = cta_arena();
     double acc[2] = {0.0, 0.0};
     GPC_FOR_2D(n, n, i, j) {
         bool cross;
@@ -150,6 +151,7 @@ __device__ void unpack_lq(int mv, const double* packed, double* Lq) {
 
 // gauss_kl (whitened): 0.5 (|q_mu|^2 - Mv + |tril(Lq)|_F^2 - sum log Lq_ii^2)
 __device__ double kl_white(int mv, const double* q_mu, const double* packed, CtaSmem* sm) {
+    sm = cta_arena();
     double acc[3] = {0.0, 0.0, 0.0};
     for (int i = threadIdx.x; i < mv; i += GPC_THREADS) {
         acc[0] = fma(q_mu[i], q_mu[i], acc[0]);
@@ -166,6 +168,7 @@ __device__ double kl_white(int mv, const double* q_mu, const double* packed, Cta
 __device__ void lik_pass(const ModelDev& md, const Hyper& h, int N, const double* fmean, const double* fvar,
                          const double* y, const double* scale, double* gm, double* gv, double& ve, double& dalpha,
                          double& dkm, CtaSmem* sm) {
+    sm = cta_arena();
     LikParams lp;
     lik_setup(lp, md.lik, h.alpha, h.km);
     double acc[3] = {0.0, 0.0, 0.0};
@@ -186,6 +189,7 @@ __device__ void lik_pass(const ModelDev& md, const Hyper& h, int N, const double
 // ------------------------------------------------------------------------------------------------ VGP
 __device__ __noinline__ int eval_vgp(const ModelDev& md, const double* y, const double* scale, const double* theta, double* grad,
                         double* f_out, const SlotWs& ws, CtaSmem* sm) {
+    sm = cta_arena();
     const int N = md.N, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const Hyper h = hyper_from_theta(md, theta);
     KernParams kp;
@@ -256,6 +260,7 @@ __device__ __noinline__ int eval_vgp(const ModelDev& md, const double* y, const 
 // ------------------------------------------------------------------------------------------------ SVGP
 __device__ __noinline__ int eval_svgp(const ModelDev& md, const double* Z, const double* y, const double* scale,
                          const double* theta, double* grad, double* f_out, const SlotWs& ws, CtaSmem* sm) {
+    sm = cta_arena();
     const int N = md.N, M = md.M, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const Hyper h = hyper_from_theta(md, theta);
     KernParams kp;
@@ -352,6 +357,7 @@ __device__ __noinline__ int eval_svgp(const ModelDev& md, const double* Z, const
 // log N(y | 0, K + noise I);  theta = (var, ls, noise, -)
 __device__ __noinline__ int eval_gpr(const ModelDev& md, const double* y, const double* theta, double* grad, double* f_out,
                         const SlotWs& ws, CtaSmem* sm) {
+    sm = cta_arena();
     const int N = md.N, tid = threadIdx.x;
     const Hyper h = hyper_from_theta(md, theta);
     KernParams kp;
@@ -396,6 +402,7 @@ __device__ __noinline__ int eval_gpr(const ModelDev& md, const double* y, const 
 // theta = (var, ls, noise s2, -); reverse pass through both Cholesky factors.
 __device__ __noinline__ int eval_sgpr(const ModelDev& md, const double* Z, const double* y, const double* theta,
                                       double* grad, double* f_out, const SlotWs& ws, CtaSmem* sm) {
+    sm = cta_arena();
     const int N = md.N, M = md.M, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const Hyper h = hyper_from_theta(md, theta);
     KernParams kp;
@@ -518,22 +525,20 @@ __device__ __noinline__ int model_eval_direct(const ModelDev& md, const double* 
 #endif
 }
 
-// The optimiser calls the evaluator through a pointer: an indirect call is compiled to the plain ABI, so the register
-// allocation of the evaluators (cta_gemm above all) does not depend on how many values the calling kernel keeps live
-// across the call.  Called directly from k_fit, ptxas' interprocedural allocation left cta_gemm spilling inside its
-// panel loop under the 128-register cap of the dense instantiation (10 local loads per panel at L2 latency).
-#ifdef GPC_DENSE_ONLY
+// The kernels call the evaluator through a device function pointer.  An indirect call is compiled to the plain ABI
+// (callee-saved registers stored once on entry, restored on exit), which makes the evaluators' register allocation
+// independent of the calling kernel.  Called directly, ptxas' interprocedural allocation gave every kernel its own
+// clone of each evaluator whose quality depended on unrelated code of that kernel: `cta_gemm` reloaded ~10 spilled
+// values per k-panel inside `k_fit` under the 128-register cap of the dense instantiation (L2 round trips), and the
+// fused evaluator ran 20-35 % slower inside `k_fit` than in `k_elbo_grad`.  The price of the ABI is that address
+// spaces are no longer inferred across the call: evaluators re-derive their shared-memory arena from `g_smem`
+// (a generic `sm` / `fs` argument would turn every LDS/STS into a generic load / store).
 typedef int (*ModelEvalFn)(const ModelDev&, const double*, const double*, const double*, const double*, double*, double*,
                            const SlotWs&, CtaSmem*);
 __device__ ModelEvalFn g_model_eval = model_eval_direct;
-#endif
 
 __device__ __forceinline__ int model_eval(const ModelDev& md, const double* Z, const double* y, const double* scale,
                           const double* theta, double* grad, double* f_out, const SlotWs& ws, CtaSmem* sm) {
-#ifdef GPC_DENSE_ONLY
     ModelEvalFn fn = *(volatile ModelEvalFn*)&g_model_eval;
     return fn(md, Z, y, scale, theta, grad, f_out, ws, sm);
-#else
-    return model_eval_direct(md, Z, y, scale, theta, grad, f_out, ws, sm);
-#endif
 }

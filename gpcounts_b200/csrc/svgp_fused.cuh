@@ -3,15 +3,15 @@
 // the N data points resident in shared memory; HBM sees only y / scale / X / Z / theta in and the gradient out.
 //
 // Math: SURVEY.md appendix B.2 (reverse pass of gpflow SVGP.elbo -> base_conditional + gauss_kl, whitened;
-// reference call site GPcounts_Module.py:679-680).  Per 64-column tile of the data:
-//     Kuf -> A = Lm^-1 Kuf -> B = Lq^T A -> (fmean, fvar) -> 20-node quadrature -> (g_m, g_v)
-//     Bbar = 2 B diag(g_v);  Abar = q_mu g_m^T - 2 A diag(g_v) + Lq Bbar;  S = Lm^-T Abar
-//     GLq += A Bbar^T (lower);  GLm += S A^T (lower);  gq += A g_m;  <S o Kuf, R^2>, <Abar, A>
-// The triangular solves are products with the explicit inverse of the 64 x 64 factor (formed once per
-// evaluation in shared memory); all six products per tile run on the FP64 tensor pipe (DMMA m8n8k4), one
-// 8-row block of the output per warp so that the triangular k-ranges are warp-uniform.  The two rank updates
-// keep their accumulators in registers across tiles and are paired (row block w with row block nrb-1-w) so
-// every warp does the same amount of work.
+// reference call site GPcounts_Module.py:679-680), rearranged around W = Lq Lq^T - I (formed once per evaluation) so
+// that a 64-column tile of the data needs 2.5 instead of 3 full M x M x 64 products and no B / Abar / S tiles:
+//     Kuf -> A = Lm^-1 Kuf -> C = W A -> fmean = A^T q_mu, fvar = kdiag + colsum(A o C) -> 20-node quadrature -> (g_m, g_v)
+//     gq += A g_m;   H += A diag(2 g_v) A^T (lower tiles);   <Abar, A> = sum_n g_m fmean + 2 g_v (fvar - kdiag)
+//     RBF only:  S = u g_m^T + (Lm^-T C) diag(2 g_v) with u = Lm^-T q_mu, consumed in registers for <S o Kuf, R^2>
+// and after the last tile  grad Lq = tril(H Lq) - (Lq - diag(1/Lq_ii)),  Lm-bar = -tril(Lm^-T (q_mu gq^T + W H)).
+// The triangular solves are products with the explicit inverse of the 64 x 64 factor (formed once per evaluation in
+// shared memory); all products run on the FP64 tensor pipe (DMMA m8n8k4), one 8-row block of the output per warp so
+// that the triangular k-ranges are warp-uniform, row blocks paired (w, nrb-1-w) so that every warp does the same work.
 #pragma once
 #include "model.cuh"
 
@@ -24,16 +24,18 @@
 #define FZ_LPC (GPC_THREADS / 64)   // lanes per data column in the statistics / quadrature phase: 4 or 8
 #define FZ_RPT (64 / FZ_LPC)        // rows per thread when a thread owns a column: 16 or 8
 
+static_assert(FZ_WPR == 1, "the fused evaluator is written for 8 warps (256 threads)");
+
 struct FusedSmem {
-    double T0[FZ_MAT];              // Kuf tile            (end phase: Kuu0 / scratch)
-    double T1[FZ_MAT];              // A tile              (end phase: GLq / P / Kbar)
-    double T2[FZ_MAT];              // B, Bbar, then S     (end phase: Lm)
-    double T3[FZ_MAT];              // Abar                (end phase: Lm-bar / T)
+    double T0[FZ_MAT];              // Kuf tile            (end phase: Lq)
+    double T1[FZ_MAT];              // A tile              (setup: Lq; end phase: H / Lm-bar / T)
+    double T2[FZ_MAT];              // C = W A             (end phase: GLq / Lm)
+    double T3[FZ_MAT];              // Kuf o R^2           (end phase: G / P / Kbar)
     double Linv[FZ_MAT];            // Lm^-1 (lower)
-    double Lq[FZ_MAT];              // tril(q_sqrt)
+    double W[FZ_MAT];               // Lq Lq^T - I (symmetric)
     double qmu[64];
     double gq[2 * FZ_WPR][64];      // A g_m accumulators, one per column group of a tile (deterministic sums)
-    double col[8][64];              // per column: fmean, fvar, gm, gv, y, scale, 2*gv, -
+    double col[8][64];              // per column: -, -, gm, -, y, scale, 2*gv; [7] = u = Lm^-T q_mu (per row)
     double red[64];
     double Zs[64 * 2];              // inducing inputs (d <= 2)
     double Xs[64 * 2];              // inputs of the current column tile
@@ -278,6 +280,10 @@ __device__ __forceinline__ LikPart lik_nodes(const LikParams& lp, double fm, dou
 __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const double* Z, const double* y,
                                                     const double* scale, const double* theta, double* grad,
                                                     double* f_out, const SlotWs& ws, FusedSmem* fs) {
+    // the arena is the start of the dynamic shared memory in every kernel of this library; re-deriving the pointer here
+    // (instead of trusting the generic `fs` argument) lets the compiler emit shared-window loads and stores even when
+    // this function is reached through a function pointer (plain ABI, no interprocedural address-space inference)
+    fs = reinterpret_cast<FusedSmem*>(g_smem);
     const int N = md.N, M = md.M, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nrb = (M + 7) >> 3, Mp = nrb * 8;          // 8-row blocks in use
     if (tid == 0) {
@@ -294,8 +300,9 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
     const double kdiag = kp.var + (md.kernel == GPC_BRANCH ? GPC_BRANCH_NOISE : 0.0);
     const bool need_kg = (md.train_mask & 3) != 0;
     const int dd = md.d;
+    const bool need_s = need_kg && md.kernel != GPC_CONST;    // S = Kuf-bar is only needed for d/d lengthscale
 
-    // ---- setup: Z, q_mu, Lq, Kuu -> Lm -> Linv ----------------------------------------------------------------
+    // ---- setup: Z, q_mu, Lq -> W = Lq Lq^T - I, Kuu -> Lm -> Linv, u = Linv^T q_mu --------------------------------
     for (int i = tid; i < 64 * 2; i += GPC_THREADS) fs->Zs[i] = (i < M * dd) ? Z[i] : 0.0;
     if (tid < 64) {
         fs->qmu[tid] = tid < M ? q_mu[tid] : 0.0;
@@ -306,7 +313,7 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
 #pragma unroll 4
     for (int idx = tid; idx < 64 * 64; idx += GPC_THREADS) {
         const int i = idx >> 6, j = idx & 63;
-        double lq = (i == j) ? 1.0 : 0.0, kv = 0.0;
+        double lq = (i == j) ? 1.0 : 0.0, kv = 0.0;       // identity padding: W = 0 outside the leading M x M block
         if (i < M && j < M) {
             lq = (j <= i) ? lq_packed[tri_index(i, j)] : 0.0;
             if (j <= i) {
@@ -315,8 +322,22 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
                 kv = kern_val(kp, r2, cross) + (i == j ? shift : 0.0);
             }
         }
-        fs->Lq[i * FZ_LD + j] = lq;
+        fs->T1[i * FZ_LD + j] = lq;
         fs->T2[i * FZ_LD + j] = kv;
+    }
+    __syncthreads();
+    {
+        // W[i][j] = sum_{k <= min(i, j)} Lq[i][k] Lq[j][k] - delta_ij   (row block `warp`, all column tiles)
+        double acc[8][2];
+        acc_zero(acc);
+        warp_mma<false, true, false>(acc, fs->T1, warp * 8, fs->T1, 0, warp * 8 + 8, 0, 8);
+        const int ar = lane >> 2, ac = 2 * (lane & 3), i = warp * 8 + ar;
+#pragma unroll
+        for (int ct = 0; ct < 8; ++ct) {
+            const int j = ct * 8 + ac;
+            *reinterpret_cast<double2*>(&fs->W[i * FZ_LD + j]) =
+                make_double2(acc[ct][0] - (i == j ? 1.0 : 0.0), acc[ct][1] - (i == j + 1 ? 1.0 : 0.0));
+        }
     }
     if (!fz_chol(fs->T2, M)) return GPC_ST_CHOL;
     fz_tri_inverse(fs->T2, M, fs->Linv);
@@ -326,17 +347,32 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
             ws.L[idx] = (i < M && j <= i) ? fs->T2[i * FZ_LD + j] : 0.0;
         }
     }
+    if (tid < 64) {                                                 // u = Linv^T q_mu
+        double u = 0.0;
+        for (int k = tid; k < Mp; ++k) u = fma(fs->Linv[k * FZ_LD + tid], fs->qmu[k], u);
+        fs->col[7][tid] = u;
+    }
 
     // ---- column tiles -------------------------------------------------------------------------------------------
-    // M x 64 products: the FZ_WPR warps of pair p own row block p for column tiles 0..3 and row block nrb-1-p for
-    // column tiles 4..7 (FZ_TPH tiles each), which balances the triangular k-ranges (cost rb+1 resp. nrb-rb).
-    double accLq[FZ_RT][2], accLm[FZ_RT][2];
-    accT_zero<FZ_RT>(accLq);
-    accT_zero<FZ_RT>(accLm);
-    const int pr = warp / FZ_WPR, hw = warp % FZ_WPR;
+    // M x 64 products: warp p owns row block p for column tiles 0..3 and row block nrb-1-p for column tiles 4..7,
+    // which balances the triangular k-ranges (cost rb+1 resp. nrb-rb).  The rank update H += (A D) A^T (lower tiles
+    // only) is balanced the same way: the two warps of a pair (p, nrb-1-p) split the nrb+1 tiles of their two row
+    // blocks - segment A = own row block (the low warp takes all its tiles, the high warp the tiles the low one
+    // leaves), segment B = the first tiles of the partner's row block (low warp only).
+    const int pr = warp;
     const bool active = pr < nrb;
     const int rA = pr * 8, rB = (nrb - 1 - pr) * 8;
-    const int ctA = hw * FZ_TPH, ctB = 4 + hw * FZ_TPH;
+    const int ctA = 0, ctB = 4;
+    const int partner = nrb - 1 - pr, share = (nrb + 2) >> 1;          // ceil((nrb + 1) / 2) tiles per warp
+    int hA0 = 0, hA1 = 0, hB1 = 0;                                      // segment A: tiles [hA0, hA1); segment B: [0, hB1)
+    if (active) {
+        if (pr < partner) { hA0 = 0; hA1 = pr + 1; hB1 = max(0, share - (pr + 1)); }
+        else if (pr == partner) { hA0 = 0; hA1 = pr + 1; }
+        else { hA0 = max(0, share - (partner + 1)); hA1 = pr + 1; }
+    }
+    double accHA[4][2], accHB[4][2];      // at most 4 tiles per segment for every nrb <= 8
+    accT_zero<4>(accHA);
+    accT_zero<4>(accHB);
     double sum_ve = 0.0, sum_da = 0.0, sum_dk = 0.0, sum_gv = 0.0, sum_sk = 0.0, sum_skr = 0.0;
     // node-independent likelihood terms (lgamma / digamma of k + y) of all N points in one converged pass: inside the
     // tile loop they would run on 8 of a warp's 32 lanes, three serialised special-function calls per tile
@@ -373,7 +409,7 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
 #pragma unroll
             for (int t = 0; t < FZ_RPT; ++t) {
                 const int i = ib + FZ_LPC * t;
-                double kv = 0.0;
+                double kv = 0.0, kr = 0.0;
                 if (cv && i < M) {
                     if (is_const) {
                         kv = kp.var;
@@ -382,9 +418,11 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
                         double r2 = u * u;
                         if (dd > 1) { const double v = fs->Zs[i * dd + 1] - x1; r2 = fma(v, v, r2); }
                         kv = kp.var * exp(ce * r2);
+                        kr = kv * r2;
                     }
                 }
                 fs->T0[i * FZ_LD + c] = kv;
+                if (need_s) fs->T3[i * FZ_LD + c] = kr;      // Kuf o R^2, for d/d lengthscale
             }
         }
         __syncthreads();
@@ -398,36 +436,35 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
             accT_store<FZ_TPH>(acc2, fs->T1, rB, ctB);
         }
         __syncthreads();
-        // ---- B = Lq^T * A (k >= row) -> T2 ------------------------------------------------------------------------
+        // ---- C = W * A (full k-range) -> T2 ------------------------------------------------------------------------
         if (active) {
             accT_zero<FZ_TPH>(acc); accT_zero<FZ_TPH>(acc2);
-            warp_mmaT<true, false, FZ_TPH>(acc, fs->Lq, rA, fs->T1, rA, Mp, ctA);
-            warp_mmaT<true, false, FZ_TPH>(acc2, fs->Lq, rB, fs->T1, rB, Mp, ctB);
+            warp_mmaT<false, false, FZ_TPH>(acc, fs->W, rA, fs->T1, 0, Mp, ctA);
+            warp_mmaT<false, false, FZ_TPH>(acc2, fs->W, rB, fs->T1, 0, Mp, ctB);
             accT_store<FZ_TPH>(acc, fs->T2, rA, ctA);
             accT_store<FZ_TPH>(acc2, fs->T2, rB, ctB);
         }
         __syncthreads();
         // ---- per-column statistics + quadrature: FZ_LPC adjacent lanes per column ---------------------------------
+        //   fmean = a . q_mu,  fvar = kdiag + a . (W a)
         {
             const int c = tid / FZ_LPC, part = tid % FZ_LPC;
-            double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            double s1 = 0.0, s2 = 0.0;
 #pragma unroll
             for (int t = 0; t < FZ_RPT; ++t) {
                 const int i = part + FZ_LPC * t;
                 if (i < Mp) {
-                    const double a = fs->T1[i * FZ_LD + c], b = fs->T2[i * FZ_LD + c];
+                    const double a = fs->T1[i * FZ_LD + c];
                     s1 = fma(a, fs->qmu[i], s1);
-                    s2 = fma(a, a, s2);
-                    s3 = fma(b, b, s3);
+                    s2 = fma(a, fs->T2[i * FZ_LD + c], s2);
                 }
             }
 #pragma unroll
             for (int o = 1; o < FZ_LPC; o <<= 1) {
                 s1 += __shfl_xor_sync(0xffffffffu, s1, o);
                 s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                s3 += __shfl_xor_sync(0xffffffffu, s3, o);
             }
-            const double fm = s1, fv = (kdiag - s2) + s3, yy = fs->col[4][c];
+            const double fm = s1, fv = kdiag + s2, yy = fs->col[4][c];
             double ve = 0.0, gm = 0.0, gz = 0.0, da = 0.0, dk = 0.0;
             bool poison = false;
             if (c < nt) {
@@ -458,70 +495,67 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
                 fs->col[2][c] = gm;
                 fs->col[6][c] = 2.0 * gv;
                 sum_gv += gv;
+                // <Abar, A> = sum_n g_m fmean + 2 g_v a.(W a)   (= <S, Kuf>: d/d variance of the cross-covariance)
+                sum_sk += gm * fm + 2.0 * gv * s2;
             }
         }
         __syncthreads();
-        // ---- Abar = q_mu gm^T - A diag(2 gv) + (Lq * B) diag(2 gv) -> T3;  gq += A gm;  <Abar, A> -------------------
+        // ---- gq += A gm;  S = u gm^T + (Linv^T C) diag(2 gv) in registers -> <S o Kuf, R^2> ---------------------------
         if (active) {
-            accT_zero<FZ_TPH>(acc); accT_zero<FZ_TPH>(acc2);
-            warp_mmaT<false, false, FZ_TPH>(acc, fs->Lq, rA, fs->T2, 0, rA + 8, ctA);
-            warp_mmaT<false, false, FZ_TPH>(acc2, fs->Lq, rB, fs->T2, 0, rB + 8, ctB);
-            double sab = 0.0, gqa = 0.0, gqb = 0.0;
+            if (need_s) {
+                accT_zero<FZ_TPH>(acc); accT_zero<FZ_TPH>(acc2);
+                warp_mmaT<true, false, FZ_TPH>(acc, fs->Linv, rA, fs->T2, rA, Mp, ctA);
+                warp_mmaT<true, false, FZ_TPH>(acc2, fs->Linv, rB, fs->T2, rB, Mp, ctB);
+            }
+            double gqa = 0.0, gqb = 0.0;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int r = (half ? rB : rA) + ar;
-                const double qm = fs->qmu[r];
                 double gql = 0.0;
+                const double ur = fs->col[7][r];
 #pragma unroll
                 for (int t = 0; t < FZ_TPH; ++t) {
                     const int c = ((half ? ctB : ctA) + t) * 8 + ac;
                     const double2 a = *reinterpret_cast<const double2*>(&fs->T1[r * FZ_LD + c]);
-                    const double g0 = fs->col[2][c], g1 = fs->col[2][c + 1], w0 = fs->col[6][c], w1 = fs->col[6][c + 1];
-                    const double p0 = half ? acc2[t][0] : acc[t][0], p1 = half ? acc2[t][1] : acc[t][1];
-                    const double v0 = (p0 - a.x) * w0 + qm * g0;
-                    const double v1 = (p1 - a.y) * w1 + qm * g1;
-                    sab = fma(v0, a.x, sab);
-                    sab = fma(v1, a.y, sab);
+                    const double g0 = fs->col[2][c], g1 = fs->col[2][c + 1];
                     gql = fma(a.x, g0, gql);
                     gql = fma(a.y, g1, gql);
-                    *reinterpret_cast<double2*>(&fs->T3[r * FZ_LD + c]) = make_double2(v0, v1);
+                    if (need_s) {
+                        const double w0 = fs->col[6][c], w1 = fs->col[6][c + 1];
+                        const double p0 = half ? acc2[t][0] : acc[t][0], p1 = half ? acc2[t][1] : acc[t][1];
+                        const double2 kr = *reinterpret_cast<const double2*>(&fs->T3[r * FZ_LD + c]);
+                        sum_skr = fma(fma(p0, w0, ur * g0), kr.x, sum_skr);
+                        sum_skr = fma(fma(p1, w1, ur * g1), kr.y, sum_skr);
+                    }
                 }
                 if (half) gqb = gql; else gqa = gql;
             }
-            sum_sk += sab;                                   // <Abar, A> = <S, Kuf>
             gqa += __shfl_xor_sync(0xffffffffu, gqa, 1); gqa += __shfl_xor_sync(0xffffffffu, gqa, 2);
             gqb += __shfl_xor_sync(0xffffffffu, gqb, 1); gqb += __shfl_xor_sync(0xffffffffu, gqb, 2);
             // each (row, column group) partial sum has exactly one writer
-            if ((lane & 3) == 0) { fs->gq[hw][rA + ar] += gqa; fs->gq[FZ_WPR + hw][rB + ar] += gqb; }
-        }
-        // ---- GLq += (A diag(2 gv)) * B^T   (row block p, column tiles hw, hw + FZ_WPR, ... <= p) ------------------------
-        if (active) warp_mma_rank(accLq, fs->T1, rA, fs->T2, fs->col[6], hw, pr + 1);
-        __syncthreads();
-        if (need_kg) {
-            // ---- S = Linv^T * Abar (k >= row) -> T2 ----------------------------------------------------------------
-            if (active) {
-                accT_zero<FZ_TPH>(acc); accT_zero<FZ_TPH>(acc2);
-                warp_mmaT<true, false, FZ_TPH>(acc, fs->Linv, rA, fs->T3, rA, Mp, ctA);
-                warp_mmaT<true, false, FZ_TPH>(acc2, fs->Linv, rB, fs->T3, rB, Mp, ctB);
-                accT_store<FZ_TPH>(acc, fs->T2, rA, ctA);
-                accT_store<FZ_TPH>(acc2, fs->T2, rB, ctB);
-            }
-            __syncthreads();
-            // ---- GLm += S * A^T (row block nrb-1-p, its column tiles);  <S o Kuf, R^2> ---------------------------------
-            if (active) warp_mma_rank(accLm, fs->T2, rB, fs->T1, nullptr, hw, nrb - pr);
-            if (md.kernel != GPC_CONST) {
-                const int c = tid & 63, ib = tid >> 6;
-                const double* xc = fs->Xs + c * dd;
-                if (c < nt) {
-                    const double x0 = xc[0], x1 = dd > 1 ? xc[1] : 0.0;
+            if ((lane & 3) == 0) { fs->gq[0][rA + ar] += gqa; fs->gq[1][rB + ar] += gqb; }
+            // ---- H += (A diag(2 gv)) A^T, lower tiles ---------------------------------------------------------------
+            {
+                const int ak = lane & 3;
+#pragma unroll 2
+                for (int k0 = 0; k0 < 64; k0 += 4) {
+                    const double sc = fs->col[6][k0 + ak];
+                    const double a1 = fs->T1[(rA + ar) * FZ_LD + k0 + ak] * sc;
 #pragma unroll
-                    for (int t = 0; t < FZ_RPT; ++t) {
-                        const int i = ib + FZ_LPC * t;
-                        if (i < M) {
-                            const double u = fs->Zs[i * dd] - x0;
-                            double r2 = u * u;
-                            if (dd > 1) { const double v = fs->Zs[i * dd + 1] - x1; r2 = fma(v, v, r2); }
-                            sum_skr = fma(fs->T2[i * FZ_LD + c] * fs->T0[i * FZ_LD + c], r2, sum_skr);
+                    for (int t = 0; t < 4; ++t) {
+                        if (hA0 + t < hA1) {
+                            const double bb = fs->T1[((hA0 + t) * 8 + ar) * FZ_LD + k0 + ak];
+                            dmma884(accHA[t], a1, bb);
+                        }
+                    }
+                    if (hB1 > 0) {
+                        const double a2 = fs->T1[(rB + ar) * FZ_LD + k0 + ak] * sc;
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            if (t < hB1) {
+                                const double bb = fs->T1[(t * 8 + ar) * FZ_LD + k0 + ak];
+                                dmma884(accHB[t], a2, bb);
+                            }
                         }
                     }
                 }
@@ -530,21 +564,54 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
     }
     __syncthreads();
     // ---- end phase ------------------------------------------------------------------------------------------------
+    // H (symmetric) -> T1;  Lq -> T0
     for (int idx = tid; idx < 64 * 64; idx += GPC_THREADS) {
         const int i = idx >> 6, j = idx & 63;
         fs->T1[i * FZ_LD + j] = 0.0;
-        fs->T3[i * FZ_LD + j] = 0.0;
+        fs->T0[i * FZ_LD + j] = (i < M && j <= i) ? lq_packed[tri_index(i, j)] : 0.0;
     }
     __syncthreads();
     if (active) {
-        const int ar2 = lane >> 2, ac2 = 2 * (lane & 3);
 #pragma unroll
-        for (int t = 0; t < FZ_RT; ++t) {
-            const int ct = hw + t * FZ_WPR;
-            if (ct <= pr)
-                *reinterpret_cast<double2*>(&fs->T1[(rA + ar2) * FZ_LD + ct * 8 + ac2]) = make_double2(accLq[t][0], accLq[t][1]);
-            if (ct < nrb - pr)
-                *reinterpret_cast<double2*>(&fs->T3[(rB + ar2) * FZ_LD + ct * 8 + ac2]) = make_double2(accLm[t][0], accLm[t][1]);
+        for (int t = 0; t < 4; ++t) {
+            if (hA0 + t < hA1) {
+                const int i = rA + ar, j = (hA0 + t) * 8 + ac;
+                fs->T1[i * FZ_LD + j] = accHA[t][0]; fs->T1[i * FZ_LD + j + 1] = accHA[t][1];
+                if (hA0 + t < pr) { fs->T1[j * FZ_LD + i] = accHA[t][0]; fs->T1[(j + 1) * FZ_LD + i] = accHA[t][1]; }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (t < hB1) {
+                const int i = rB + ar, j = t * 8 + ac;
+                fs->T1[i * FZ_LD + j] = accHB[t][0]; fs->T1[i * FZ_LD + j + 1] = accHB[t][1];
+                fs->T1[j * FZ_LD + i] = accHB[t][0]; fs->T1[(j + 1) * FZ_LD + i] = accHB[t][1];   // t < partner: off-diagonal
+            }
+        }
+    }
+    __syncthreads();
+    {
+        // GLq = tril(H Lq) -> T2;   G = W H + q_mu gq^T -> T3   (row block `warp`)
+        double acc[8][2];
+        const int r0 = warp * 8;
+        if (active) {
+            acc_zero(acc);
+            warp_mma<false, false, true>(acc, fs->T1, r0, fs->T0, 0, Mp, 0, warp + 1);
+            acc_store(acc, fs->T2, r0, 0, warp + 1);
+            if (need_kg) {
+                acc_zero(acc);
+                warp_mma<false, false, false>(acc, fs->W, r0, fs->T1, 0, Mp, 0, nrb);
+                const double qm = fs->qmu[r0 + ar];
+#pragma unroll
+                for (int ct = 0; ct < 8; ++ct) {
+                    const int j = ct * 8 + ac;
+                    if (ct < nrb) {
+                        const double g0 = fs->gq[0][j] + fs->gq[1][j], g1 = fs->gq[0][j + 1] + fs->gq[1][j + 1];
+                        *reinterpret_cast<double2*>(&fs->T3[(r0 + ar) * FZ_LD + j]) =
+                            make_double2(fma(qm, g0, acc[ct][0]), fma(qm, g1, acc[ct][1]));
+                    }
+                }
+            }
         }
     }
     __syncthreads();
@@ -552,65 +619,72 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
     for (int idx = tid; idx < M * M; idx += GPC_THREADS) {
         const int i = idx / M, j = idx % M;
         if (j <= i) {
-            const double l = fs->Lq[i * FZ_LD + j];
-            glq[tri_index(i, j)] = fs->T1[i * FZ_LD + j] - (i == j ? l - 1.0 / l : l);
+            const double l = fs->T0[i * FZ_LD + j];
+            glq[tri_index(i, j)] = fs->T2[i * FZ_LD + j] - (i == j ? l - 1.0 / l : l);
         }
     }
-    if (tid < M) {
-        double gsum = 0.0;
-#pragma unroll
-        for (int q = 0; q < 2 * FZ_WPR; ++q) gsum += fs->gq[q][tid];
-        grad[GPC_NHYP + tid] = gsum - fs->qmu[tid];
-    }
+    if (tid < M) grad[GPC_NHYP + tid] = (fs->gq[0][tid] + fs->gq[1][tid]) - fs->qmu[tid];
     double acc6[6] = {sum_ve, sum_da, sum_dk, sum_gv, sum_sk, sum_skr};
     cta_sum_n<6>(acc6, fs->red);
     double klacc[3] = {0.0, 0.0, 0.0};
     for (int idx = tid; idx < M * M; idx += GPC_THREADS) {
         const int i = idx / M, j = idx % M;
-        if (j <= i) { const double l = fs->Lq[i * FZ_LD + j]; klacc[1] = fma(l, l, klacc[1]); if (i == j) klacc[2] += log(l * l); }
+        if (j <= i) { const double l = fs->T0[i * FZ_LD + j]; klacc[1] = fma(l, l, klacc[1]); if (i == j) klacc[2] += log(l * l); }
     }
     if (tid < M) klacc[0] = fs->qmu[tid] * fs->qmu[tid];
     cta_sum_n<3>(klacc, fs->red);
     const double kl = 0.5 * (klacc[0] - (double)M + klacc[1] - klacc[2]);
     double gvar = 0.0, gls = 0.0;
     if (need_kg) {
-        // Lm -> T2;  Lm-bar = -tril(GLm) -> T3 (lower, zero upper)
+        double acc[8][2];
+        const int r0 = warp * 8;
+        // Lm-bar = -tril(Linv^T G) -> T1 (lower, zero upper):  (Linv^T G)[i][j] = sum_{k >= i} Linv[k][i] G[k][j]
+        if (active) {
+            acc_zero(acc);
+            warp_mma<true, false, false>(acc, fs->Linv, r0, fs->T3, r0, Mp, 0, warp + 1);
+        }
+        __syncthreads();          // every warp has read H (T1) and G (T3)
+        if (active) {
+#pragma unroll
+            for (int ct = 0; ct < 8; ++ct) {
+                const int i = r0 + ar, j = ct * 8 + ac;
+                const double v0 = (ct <= warp && j <= i) ? -acc[ct][0] : 0.0;
+                const double v1 = (ct <= warp && j + 1 <= i) ? -acc[ct][1] : 0.0;
+                *reinterpret_cast<double2*>(&fs->T1[i * FZ_LD + j]) = make_double2(v0, v1);
+            }
+        }
+        // Lm -> T2
         for (int idx = tid; idx < 64 * 64; idx += GPC_THREADS) {
             const int i = idx >> 6, j = idx & 63;
             fs->T2[i * FZ_LD + j] = ws.L[idx];
-            const double v = fs->T3[i * FZ_LD + j];
-            fs->T3[i * FZ_LD + j] = (j <= i) ? -v : 0.0;
         }
         __syncthreads();
-        double acc[8][2];
-        const int r0 = warp * 8;
-        const bool active = warp < nrb;
-        // P = Phi(Lm^T * Lmbar) -> T1 (lower):  P[i][j] = sum_{k >= i} Lm[k][i] Lmbar[k][j]
+        // P = Phi(Lm^T * Lmbar) -> T3 (lower):  P[i][j] = sum_{k >= i} Lm[k][i] Lmbar[k][j]
         if (active) {
             acc_zero(acc);
-            warp_mma<true, false, false>(acc, fs->T2, r0, fs->T3, r0, Mp, 0, warp + 1);
+            warp_mma<true, false, false>(acc, fs->T2, r0, fs->T1, r0, Mp, 0, warp + 1);
 #pragma unroll
             for (int ct = 0; ct < 8; ++ct) {
                 const int i = r0 + ar, j = ct * 8 + ac;
                 double v0 = (ct <= warp) ? acc[ct][0] : 0.0, v1 = (ct <= warp) ? acc[ct][1] : 0.0;
                 v0 = (j < i) ? v0 : (j == i ? 0.5 * v0 : 0.0);
                 v1 = (j + 1 < i) ? v1 : (j + 1 == i ? 0.5 * v1 : 0.0);
-                *reinterpret_cast<double2*>(&fs->T1[i * FZ_LD + j]) = make_double2(v0, v1);
+                *reinterpret_cast<double2*>(&fs->T3[i * FZ_LD + j]) = make_double2(v0, v1);
             }
         }
         __syncthreads();
-        // T = Linv^T * P -> T3:  T[i][j] = sum_{k >= max(i, j)} Linv[k][i] P[k][j]
+        // T = Linv^T * P -> T1:  T[i][j] = sum_{k >= max(i, j)} Linv[k][i] P[k][j]
         if (active) {
             acc_zero(acc);
-            warp_mma<true, false, true>(acc, fs->Linv, r0, fs->T1, r0, Mp, 0, nrb);
-            acc_store(acc, fs->T3, r0, 0, 8);
+            warp_mma<true, false, true>(acc, fs->Linv, r0, fs->T3, r0, Mp, 0, nrb);
+            acc_store(acc, fs->T1, r0, 0, 8);
         }
         __syncthreads();
-        // Kbar = T * Linv -> T1:  Kbar[i][j] = sum_{k >= j} T[i][k] Linv[k][j]
+        // Kbar = T * Linv -> T3:  Kbar[i][j] = sum_{k >= j} T[i][k] Linv[k][j]
         if (active) {
             acc_zero(acc);
-            warp_mma<false, false, true>(acc, fs->T3, r0, fs->Linv, 0, Mp, 0, nrb);
-            acc_store(acc, fs->T1, r0, 0, 8);
+            warp_mma<false, false, true>(acc, fs->T1, r0, fs->Linv, 0, Mp, 0, nrb);
+            acc_store(acc, fs->T3, r0, 0, 8);
         }
         __syncthreads();
         double a2[2] = {0.0, 0.0};
@@ -619,7 +693,7 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
             bool cross;
             const double r2 = kern_r2(kp, fs->Zs + i * dd, fs->Zs + j * dd, cross);
             const double k0 = kern_val(kp, r2, cross);
-            kern_grad_acc(kp, fs->T1[i * FZ_LD + j], k0, r2, cross, a2[0], a2[1]);
+            kern_grad_acc(kp, fs->T3[i * FZ_LD + j], k0, r2, cross, a2[0], a2[1]);
         }
         cta_sum_n<2>(a2, fs->red);
         // RBF / Constant: d Kuf / d var = Kuf / var, so <S, dKuf/dvar> = <Abar, A> / var
