@@ -197,8 +197,10 @@ __device__ int warp_chol_upper(double* A, int lda, int n) {
         for (int j = k + 1 + lane; j < n; j += 32) A[k * lda + j] /= r;
         __syncwarp();
         const int rem = n - k - 1;
+        const unsigned inv = rem > 0 ? (65536u + rem - 1) / rem : 0u;   // exact idx / rem for idx < rem^2, rem <= 20
         for (int idx = lane; idx < rem * rem; idx += 32) {
-            const int i = k + 1 + idx / rem, j = k + 1 + idx % rem;
+            const int q = (int)(((unsigned)idx * inv) >> 16);
+            const int i = k + 1 + q, j = k + 1 + (idx - q * rem);
             if (j >= i) A[i * lda + j] -= A[k * lda + i] * A[k * lda + j];
         }
     }
@@ -416,23 +418,46 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
             if (info != 0) { col = 0; head = 0; theta = 1.0; updated = false; continue; }   // refresh the memory
             updated = false;
             const double ith = 1.0 / theta;
-            for (int i = tid; i < P; i += GPC_THREADS) {
-                const double xi = ws.x[i], gi = ws.g[i];
-                double di = -gi;
+            // eight elements per thread at a time, memory pairs in the outer loop: the 16 loads of a pair are independent
+            // (a per-element j-loop serialises one L2 round trip per pair); per element the arithmetic keeps its order
+            for (int i0 = tid; i0 < P; i0 += 8 * GPC_THREADS) {
+                double xi[8], gi[8], di[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u * GPC_THREADS;
+                    xi[u] = i < P ? ws.x[i] : 0.0;
+                    gi[u] = i < P ? ws.g[i] : 0.0;
+                    di[u] = -gi[u];
+                }
                 for (int j = 0; j < col; ++j) {
                     const size_t slot = (size_t)((head + j) % m) * P;
-                    di += ws.WY[slot + i] * (os->wv[j] / theta) + ws.WS[slot + i] * os->wv[col + j];
+                    const double cy = os->wv[j] / theta, cs = os->wv[col + j];
+                    double vy[8], vs[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u * GPC_THREADS;
+                        vy[u] = i < P ? ws.WY[slot + i] : 0.0;
+                        vs[u] = i < P ? ws.WS[slot + i] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) di[u] += vy[u] * cy + vs[u] * cs;
                 }
-                di *= ith;
-                const double zi = xi + di;
-                di = zi - xi;
-                ws.z[i] = zi;
-                ws.d[i] = di;
-                ws.xold[i] = xi;
-                ws.gold[i] = gi;
-                if (first_is_z) ws.x[i] = zi;
-                acc2[0] = fma(di, di, acc2[0]);
-                acc2[1] = fma(gi, di, acc2[1]);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u * GPC_THREADS;
+                    if (i < P) {
+                        double d = di[u] * ith;
+                        const double zi = xi[u] + d;
+                        d = zi - xi[u];
+                        ws.z[i] = zi;
+                        ws.d[i] = d;
+                        ws.xold[i] = xi[u];
+                        ws.gold[i] = gi[u];
+                        if (first_is_z) ws.x[i] = zi;
+                        acc2[0] = fma(d, d, acc2[0]);
+                        acc2[1] = fma(gi[u], d, acc2[1]);
+                    }
+                }
             }
         }
         cta_sum_n<2>(acc2, sm->red);
@@ -512,14 +537,14 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
         if (!skip) {
             if (col == m) {       // drop the oldest pair: shift the small matrices
                 __syncthreads();
-                if (tid == 0) {
-                    for (int i = 0; i < m - 1; ++i)
-                        for (int j = 0; j < m - 1; ++j) {
-                            os->SS[i][j] = os->SS[i + 1][j + 1];
-                            os->SY[i][j] = os->SY[i + 1][j + 1];
-                            os->YY[i][j] = os->YY[i + 1][j + 1];
-                            os->RZ[i][j] = os->RZ[i + 1][j + 1];
-                        }
+                {
+                    // one element per thread: read (i + 1, j + 1), barrier, write (i, j)
+                    const int i = tid / GPC_MMAX, j = tid % GPC_MMAX;
+                    const bool mine = i < m - 1 && j < m - 1;
+                    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+                    if (mine) { v0 = os->SS[i + 1][j + 1]; v1 = os->SY[i + 1][j + 1]; v2 = os->YY[i + 1][j + 1]; v3 = os->RZ[i + 1][j + 1]; }
+                    __syncthreads();
+                    if (mine) { os->SS[i][j] = v0; os->SY[i][j] = v1; os->YY[i][j] = v2; os->RZ[i][j] = v3; }
                 }
                 head = (head + 1) % m;
                 col = m - 1;
