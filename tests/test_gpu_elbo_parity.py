@@ -55,6 +55,14 @@ def test_svgp(lik, kernel):
     _compare("SVGP", kernel, lik, N=150, M=20)
 
 
+@pytest.mark.parametrize("M", [5, 13, 24, 33, 41, 50, 57, 64])
+def test_svgp_fused_every_row_block_count(M):
+    """The fused evaluator splits its rank update between paired warps differently for every number of 8-row blocks
+    (1..8); N = 150 also leaves a ragged last column tile."""
+    _compare("SVGP", "RBF", "NB", N=150, M=M, D=2, seed=M)
+    _compare("SVGP", "CONST", "ZINB", N=150, M=M, D=2, seed=M + 1)
+
+
 @pytest.mark.parametrize("lik", ["NB", "ZINB", "POISSON"])
 @pytest.mark.parametrize("kernel", ["RBF", "CONST"])
 def test_vgp(lik, kernel):
