@@ -1,7 +1,11 @@
-"""Tiny end-to-end run of every kernel family for `compute-sanitizer --tool racecheck` (and memcheck):
+"""Tiny end-to-end run of every kernel family, sized for `compute-sanitizer --tool racecheck` / memcheck:
 
     python tools/racecheck_small.py                                     # must exit 0 on its own first
-    compute-sanitizer --tool racecheck python tools/racecheck_small.py
+    compute-sanitizer --tool racecheck python tools/racecheck_small.py  # where the sanitizer is available
+
+(The sanitizer is closed on the build pool of round 1; the shared-memory race this script was written to hunt - the
+diagonal overwrite in the left-looking Cholesky - was found by inspection and is covered by
+tests/test_gpu_properties.py::test_dense_path_is_reproducible_under_contention.)
 
 Fused SVGP evaluation + short fit (M = 64), dense SVGP (M = 72 > 64: two diagonal blocks), dense VGP (N = 70), GPR, SGPR."""
 import sys, numpy as np, torch
