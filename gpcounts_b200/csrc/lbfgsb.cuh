@@ -32,6 +32,7 @@ struct OptSmem {
     double dots[GPC_MMAX][6];          // per memory vector: S.d, Y.d, S.r, Y.r, S.g, Y.g
     double T[GPC_MMAX][GPC_MMAX];      // formt scratch
     int info;
+    int info_dir;                      // outcome of the direction solve (formk / subsm) done at the end of an iteration
 };
 
 struct DcsrchState {
@@ -399,22 +400,9 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
                 acc2[1] = fma(gi, di, acc2[1]);
             }
         } else {
-            if (warp == 0) {
-                int info = 0;
-                if (updated) info = formk_free(os, col, theta);
-                if (info == 0) {
-                    if (lane < col) {
-                        os->wv[lane] = -os->dots[lane][5];                 // Y_j . r, r = -g
-                        os->wv[col + lane] = -theta * os->dots[lane][4];   // theta * S_j . r
-                    }
-                    __syncwarp();
-                    subsm_solve(os, col);
-                }
-                if (lane == 0) os->info = info;
-            }
-            __syncthreads();
-            const int info = os->info;
-            __syncthreads();
+            // the middle-matrix solve for this direction was done at the end of the previous iteration (warp 1, next
+            // to formt on warp 0): every path that reaches this point with col > 0 comes from there
+            const int info = os->info_dir;
             if (info != 0) { col = 0; head = 0; theta = 1.0; updated = false; continue; }   // refresh the memory
             updated = false;
             const double ith = 1.0 / theta;
@@ -595,9 +583,26 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
                 os->SS[c][c] = (stp == 1.0) ? dtd : stp * stp * dtd;
                 os->SY[c][c] = dr;
             }
-            __syncwarp();
+        }
+        __syncthreads();
+        // formt (acceptance of the new pair) on warp 0 and, concurrently on warp 1, the direction solve of the next
+        // iteration: formk (only when a pair was stored) and subsm with the dot products of the new gradient
+        if (!skip && warp == 0) {
             const int info = formt_check(os, col, theta);
             if (lane == 0) os->info = info;
+        }
+        if (warp == 1 && col > 0) {
+            int info = 0;
+            if (updated) info = formk_free(os, col, theta);
+            if (info == 0) {
+                if (lane < col) {
+                    os->wv[lane] = -os->dots[lane][5];                 // Y_j . r, r = -g
+                    os->wv[col + lane] = -theta * os->dots[lane][4];   // theta * S_j . r
+                }
+                __syncwarp();
+                subsm_solve(os, col);
+            }
+            if (lane == 0) os->info_dir = info;
         }
         __syncthreads();
         if (!skip) {
