@@ -6,7 +6,7 @@ the ABI entry/exit saves only; this script recompiles gpc_fused.cu with `-Xptxas
 
     python tools/clone_gate.py            # exit 0 if the k_fit clone has the accepted frame
 
-Accepted (round 1, 860 genes/s): 656 B stack, 740 B spill stores, 844 B spill loads.  A different frame is not
+Accepted (round 1, 878 genes/s): 656 B stack, 740 B spill stores, 844 B spill loads.  A different frame is not
 necessarily slower - measure (`python bench.py --steps 1 --warmup 1 --no-cpu --genes 4096`, time_split.us_per_eval_in_fit
 was 386 us) and update ACCEPTED if the new one is kept.
 """
