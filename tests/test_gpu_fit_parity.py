@@ -9,10 +9,13 @@ start perturbed by 1e-12: fits whose two oracle runs agree are *stable* and must
 are only required to land on one of the oracle's answers or between them.
 
 Even a stable fit can stop early on a plateau: SciPy's rule ends the run the first time one iteration gains less than
-2.2e-9 |f|, and along a creeping valley whether that happens at iteration 240 or 450 is decided by round-off
-(measured on gene 0 of the NB fixture: 30 of 32 GPU runs from starts perturbed by k * 1e-13 end within 1e-6 of the
-oracle, 2 stop 0.008 nats short; `tools/perturb_gene.py`).  A dynamic-model mismatch is therefore re-examined: the
-median of five GPU fits from perturbed starts must match the oracle, and at most one fit per fixture may need that.
+2.2e-9 |f|, and along a creeping valley whether that happens at iteration 240 or 450 is decided by round-off.  Measured
+on gene 0 of the NB fixture, starts perturbed by k * 1e-13: the oracle (SciPy on the CPU) ends 3 of 32 runs 0.008 nats
+short at -424.2078 / -424.2076 / -424.2075, the GPU 2 of 32 at -424.2077 / -424.2076 (`tests/golden/
+make_perturbed_runs.py`, `tools/perturb_gene.py`) - a fit has a small *set* of outcomes, the same set on both sides.
+A dynamic-model mismatch is therefore re-examined: the GPU value must coincide with one of the oracle's 32 outcomes
+(`<fixture>_runs.npz`) or, failing that, the median of five GPU fits from perturbed starts must match the oracle; at
+most one fit per fixture may need either.
 """
 import os
 
@@ -57,13 +60,20 @@ def _median_of_perturbed_fits(fx, g, lik, sparse):
     return float(np.median(lls))
 
 
-def _check_table(df, fx, K, skip=None, lik=None, sparse=False):
+def _oracle_outcomes(name, g):
+    """Dynamic-model log-likelihoods of gene g over the oracle's 32 perturbed starts, if the fixture has them."""
+    path = os.path.join(GOLD, name + "_runs.npz")
+    return np.load(path)["ll_runs"][g] if os.path.exists(path) else None
+
+
+def _check_table(df, fx, K, skip=None, lik=None, sparse=False, name=None):
     got = df.values.copy()
     ref, ref2 = fx["ll"], fx["ll_pert"]
     assert got.shape == ref.shape
     n_stable = 0
     n_retried = 0
     for g in range(ref.shape[0]):
+        shift = 0.0           # oracle's alternative outcome of the dynamic fit minus its primary one (see below)
         for k in range(K):
             a, b = ref[g, k], ref2[g, k]
             stable = abs(a - b) <= 1e-6 * abs(a)
@@ -75,6 +85,10 @@ def _check_table(df, fx, K, skip=None, lik=None, sparse=False):
             if abs(got[g, k] - a) > tol and k == 0 and K == 2 and lik is not None and got[g, k] < a:
                 # an early plateau stop of the dynamic fit (lower ELBO, see the module docstring)
                 n_retried += 1
+                runs = _oracle_outcomes(name, g) if name else None
+                if runs is not None and np.abs(runs - got[g, k]).min() <= tol:
+                    shift = runs[np.abs(runs - got[g, k]).argmin()] - a     # one of the oracle's own outcomes
+                    continue
                 med = _median_of_perturbed_fits(fx, g, lik, sparse)
                 assert abs(med - a) <= tol, (g, k, got[g, k], med, a, b)
                 got[g, K] += med - got[g, k]
@@ -84,7 +98,7 @@ def _check_table(df, fx, K, skip=None, lik=None, sparse=False):
         if skip is not None and any(gg == g for gg, _ in skip):
             continue
         if abs(a - b) <= 1e-5 * abs(a) + 1e-5:
-            assert abs(got[g, K] - a) <= LLR_RTOL * abs(a) + LLR_ATOL, (g, got[g, K], a)
+            assert abs(got[g, K] - (a + shift)) <= LLR_RTOL * abs(a) + LLR_ATOL, (g, got[g, K], a, shift)
     assert n_stable >= 0.7 * ref.shape[0] * K
     assert n_retried <= 1
 
@@ -98,7 +112,7 @@ def test_one_sample_sparse(name):
     df = gp.One_sample_test(str(fx["lik"]))
     assert list(df.columns) == ["Dynamic_model_log_likelihood", "Constant_model_log_likelihood", "log_likelihood_ratio"]
     assert list(df.index) == list(Ydf.index)
-    _check_table(df, fx, 2, lik=str(fx["lik"]), sparse=True)
+    _check_table(df, fx, 2, lik=str(fx["lik"]), sparse=True, name=name)
     assert (gp.fit_stats["status"] == 0).all()
     out = gp.calculate_FDR(df)
     assert {"p_value", "q_value"} <= set(out.columns)
@@ -129,6 +143,9 @@ def test_infer_trajectory_matches_dynamic_column():
     assert bad.sum() <= 1                      # at most one early plateau stop, re-examined as in _check_table
     for g in np.nonzero(bad)[0]:
         assert df.values[g, 0] < ref[g]
+        runs = _oracle_outcomes("one_sample_sparse_nb", g)
+        if runs is not None and np.abs(runs - df.values[g, 0]).min() <= LL_RTOL * abs(ref[g]):
+            continue
         med = _median_of_perturbed_fits(fx, g, "Negative_binomial", True)
         assert abs(med - ref[g]) <= LL_RTOL * abs(ref[g]), (g, df.values[g, 0], med, ref[g])
 
