@@ -82,3 +82,18 @@ def test_poisson_quadrature_equals_closed_form():
     F = fm[None] + torch.sqrt(fv)[None] * gm.GH_Z[:, None]
     quad = (gm.GH_W[:, None] * (y[None] * F - torch.exp(F) - torch.lgamma(y + 1)[None])).sum()
     assert abs(float(closed - quad)) < 1e-10
+
+
+def test_perturbed_oracle_runs_are_consistent_with_the_fixture():
+    """tests/golden/make_perturbed_runs.py: run k = 0 is the fixture's primary run, run k = 10 (1e-12) its perturbed one;
+    the outcome set of a fit is small (a few plateau values), which is what the GPU parity tests rely on."""
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    fx = np.load(os.path.join(gold, "one_sample_sparse_nb.npz"), allow_pickle=True)
+    runs = np.load(os.path.join(gold, "one_sample_sparse_nb_runs.npz"))["ll_runs"]
+    assert runs.shape == (fx["ll"].shape[0], 32)
+    assert np.array_equal(runs[:, 0], fx["ll"][:, 0])
+    assert np.array_equal(runs[:, 10], fx["ll_pert"][:, 0])
+    spread = runs.max(1) - runs.min(1)
+    assert (spread < 1e-9).sum() >= 2           # well-posed fits reproduce to all digits
+    assert spread.max() < 0.01                  # the others move by millinats: early plateau stops
