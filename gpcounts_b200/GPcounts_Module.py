@@ -118,6 +118,7 @@ class Fit_GPcounts(object):
         self.optimizer_options = {}     # overrides of the L-BFGS-B settings (m, maxiter, maxfun, maxls, ftol, gtol)
         self.last_fit_seconds = None
         self.distributed = True         # shard genes over torch.distributed ranks when a process group is initialised
+        self._z_cache = {}
         self.inducing_per_gene = False  # True: attempt 0 uses RobustGP points selected under each gene's own initial
                                         # variance, as the reference does; default: one shared set
         if safe_mode:
@@ -258,7 +259,11 @@ class Fit_GPcounts(object):
         Z = None
         if self.sparse:
             ls0 = host.default_lengthscale(Xm) if self.user_hyper_parameters[0] is None else self.user_hyper_parameters[0]
-            Z = host.inducing_sets(Xm, self.M, ls0, with_restarts=restarts)
+            # gene-independent: one selection per (X, M, ls0), shared by the models of a test
+            key = (Xm.shape, hash(Xm.tobytes()), int(self.M), float(ls0), bool(restarts))
+            if key not in self._z_cache:
+                self._z_cache = {key: host.inducing_sets(Xm, self.M, ls0, with_restarts=restarts)}
+            Z = self._z_cache[key]
             self.Z = Z[0]
         return engine.Model(kind, kernel, lik, Xm, Z=Z, n_off=n_off, train=train, handoff_alpha=handoff, xp=xp,
                             restart=self._restart(Xm, kernel, fixed) if restarts else None, device=self._device())
@@ -300,15 +305,17 @@ class Fit_GPcounts(object):
         return stats_all.cpu().numpy()
 
     def _record_stats(self, stats, genes_index, names):
-        rows = []
-        for gi, g in enumerate(genes_index):
-            for k, nm in enumerate(names):
-                s = stats[gi, k]
-                rows.append(dict(gene=self.genes_name[g], model=nm, log_likelihood=s[S_LL], status=int(s[S_STATUS]),
-                                 n_iter=int(s[S_NIT]), n_feval=int(s[S_NFEV]), n_feval_total=int(s[S_NFEV_TOTAL]),
-                                 restarts=int(s[S_RESTARTS]), variance=s[S_VAR], lengthscale=s[S_LS],
-                                 alpha=s[S_ALPHA], km=s[S_KM]))
-        self.fit_stats = pd.DataFrame(rows)
+        """Per (gene, model) fit statistics as a DataFrame (built column-wise: no per-row Python objects)."""
+        stats = np.asarray(stats)
+        G, K = stats.shape[0], len(names)
+        flat = stats[:, :K].reshape(G * K, -1)
+        gene_names = np.asarray(self.genes_name, dtype=object)[np.asarray(list(genes_index), dtype=np.int64)]
+        self.fit_stats = pd.DataFrame({
+            "gene": np.repeat(gene_names, K), "model": np.tile(np.asarray(names, dtype=object), G),
+            "log_likelihood": flat[:, S_LL], "status": flat[:, S_STATUS].astype(np.int64),
+            "n_iter": flat[:, S_NIT].astype(np.int64), "n_feval": flat[:, S_NFEV].astype(np.int64),
+            "n_feval_total": flat[:, S_NFEV_TOTAL].astype(np.int64), "restarts": flat[:, S_RESTARTS].astype(np.int64),
+            "variance": flat[:, S_VAR], "lengthscale": flat[:, S_LS], "alpha": flat[:, S_ALPHA], "km": flat[:, S_KM]})
 
     def _set_last_model(self, models, stats, k, Xm, y, kernel="RBF", xp=None):
         """``self.model`` = model of the last gene fitted, as the reference leaves it after the loop (:264-265)."""
@@ -372,7 +379,10 @@ class Fit_GPcounts(object):
         if genes_index:
             self.y = Y[genes_index[-1]].reshape([-1, 1])
             k_last = len(models) - 1
-            self._set_last_model(models, stats, k_last, X, self.y)
+            if models_number == 3:          # the reference leaves the model of the second half behind (:477-484)
+                self._set_last_model(models, stats, k_last, X[int(self.N / 2):], self.y[int(self.N / 2):])
+            else:
+                self._set_last_model(models, stats, k_last, X, self.y)
         return pd.DataFrame(out, index=[self.genes_name[g] for g in genes_index], columns=column_name)
 
     # ------------------------------------------------------------------------------------------ branching

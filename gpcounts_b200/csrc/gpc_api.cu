@@ -5,9 +5,10 @@
 // from an atomic queue until it is empty, so genes whose optimisation takes 20 iterations and genes that
 // take 2000 share the machine without any inter-CTA synchronisation and without host round trips.
 // Genes never communicate: sharding over GPUs is a partition of the job list.
+#include <atomic>
 #include <cstdio>
 #include <cstring>
-#include <cstdlib>
+#include <mutex>
 #include <cuda_runtime.h>
 #include "../../include/gpcounts_b200.h"
 #define GPC_VARIANT t256
@@ -15,9 +16,7 @@
 
 
 static thread_local char g_err[512] = "";
-static double* g_trace = nullptr;
-static int g_trace_cap = 0, g_trace_gene = 0, g_trace_model = 0;
-static long long g_launches = 0;
+static std::atomic<long long> g_launches{0};
 
 static int set_err(int code, const char* fmt, const char* a = "") {
     snprintf(g_err, sizeof(g_err), fmt, a);
@@ -67,25 +66,26 @@ static size_t smem_bytes() { return eval_smem_bytes() + sizeof(OptSmem); }
 static VariantOps g_ops[3];
 VariantOps gpc_variant_ops_d128();     // gpc_dense.cu
 VariantOps gpc_variant_ops_f256();     // gpc_fused.cu
-static int g_force_variant = -1;       // A/B measurements: GPC_FORCE_VARIANT=0 keeps everything on instantiation [0]
 
 static bool host_use_fused(const gpc_model_t& md) {
     return md.kind == GPC_SVGP && md.M <= 64 && md.d <= 2 && md.kernel != GPC_BRANCH;
 }
 
-static int pick_variant(const gpc_model_t* models, int n_models) {
+static int pick_variant(const gpc_model_t* models, int n_models, int forced = -1) {
     bool any_fused = false, all_fused = true;
     for (int k = 0; k < n_models; ++k) {
         const bool f = host_use_fused(models[k]);
         any_fused = any_fused || f;
         all_fused = all_fused && f;
     }
-    if (g_force_variant == 0) return 0;
+    if (forced == 0) return 0;       // instantiation [0] holds every evaluator (A/B measurements through gpc_opt_t.variant)
     return all_fused ? 2 : (any_fused ? 0 : 1);
 }
 
 static int ensure_init() {
     static bool done[64] = {false};
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return set_err(GPC_E_LAUNCH, "no CUDA device%s");
     if (dev < 64 && done[dev]) return 0;
@@ -95,8 +95,6 @@ static int ensure_init() {
     g_ops[0] = gpc_variant_ops_t256();
     g_ops[1] = gpc_variant_ops_d128();
     g_ops[2] = gpc_variant_ops_f256();
-    const char* fv = getenv("GPC_FORCE_VARIANT");
-    if (fv) g_force_variant = atoi(fv);
     for (int v = 0; v < 3; ++v)
         if (g_ops[v].upload_constants(z, w) != 0)
             return set_err(GPC_E_LAUNCH, "constant upload failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -114,6 +112,8 @@ static int check_model(const gpc_model_t& md) {
     if (md.N <= 0 || md.d <= 0 || !md.X) return set_err(GPC_E_ARG, "model needs N > 0, d > 0 and X%s");
     if ((md.kind == GPC_SVGP || md.kind == GPC_SGPR) && (md.M <= 0 || !md.Z || md.n_zsets < 1))
         return set_err(GPC_E_ARG, "sparse model needs M > 0 and Z%s");
+    if ((md.kind == GPC_SVGP || md.kind == GPC_SGPR) && md.restart && md.n_zsets != 1 && md.n_zsets != 1 + GPC_MAX_RESTART)
+        return set_err(GPC_E_ARG, "a model with a restart table needs n_zsets = 1 or 1 + GPC_MAX_RESTART inducing sets%s");
     if (md.kernel == GPC_BRANCH && md.d != 2) return set_err(GPC_E_ARG, "BRANCH kernel needs d = 2 ([t, label])%s");
     return 0;
 }
@@ -123,6 +123,7 @@ extern "C" {
 void gpc_default_opt(gpc_opt_t* opt) {
     opt->m = 10; opt->maxiter = 5000; opt->maxfun = 15000; opt->maxls = 20;
     opt->ftol = 2.220446049250313e-09; opt->gtol = 1e-5;
+    opt->variant = -1; opt->trace_cap = 0; opt->trace_gene = -1; opt->trace_model = -1; opt->trace = nullptr;
 }
 
 int64_t gpc_param_count(const gpc_model_t* model) {
@@ -207,38 +208,37 @@ int gpc_fit(const gpc_model_t* models, int32_t n_models, int32_t chain, const gp
     a.queue = (int*)workspace;
     a.ws = (double*)((char*)workspace + hdr);
     a.lay = L;
-    a.trace = g_trace; a.trace_cap = g_trace_cap; a.trace_gene = g_trace_gene; a.trace_model = g_trace_model;
+    a.trace = opt->trace; a.trace_cap = opt->trace_cap; a.trace_gene = opt->trace_gene; a.trace_model = opt->trace_model;
     cudaMemsetAsync(a.queue, 0, 256, s);
     const int n_jobs = chain ? D : D * n_models;
     const int grid = n_slots < n_jobs ? n_slots : n_jobs;
-    cudaError_t e = g_ops[pick_variant(models, n_models)].launch_fit(&a, grid, s);
+    cudaError_t e = g_ops[pick_variant(models, n_models, opt->variant)].launch_fit(&a, grid, s);
     ++g_launches;
     if (e != cudaSuccess) return set_err(GPC_E_LAUNCH, "gpc_fit launch: %s", cudaGetErrorString(e));
     return 0;
 }
 
+size_t gpc_dbg_linalg_scratch_bytes(int32_t batch, int32_t n) {
+    const size_t nblk = (size_t)(n + GPC_BLK - 1) / GPC_BLK;
+    return ((size_t)nblk * GPC_BLK * GPC_BLK + (size_t)n * n) * (size_t)batch * sizeof(double);
+}
+
 int gpc_dbg_linalg(int32_t op, int32_t batch, int32_t n, int32_t nrhs, double* A, double* B, int32_t* status,
-                   void* stream) {
+                   void* scratch, size_t scratch_bytes, void* stream) {
     int rc = ensure_init();
     if (rc) return rc;
-    if (op < 0 || op > 4 || batch < 1 || n < 1 || !A || !status) return set_err(GPC_E_ARG, "gpc_dbg_linalg: bad argument%s");
-    const int nblk = (n + GPC_BLK - 1) / GPC_BLK;
-    double* scratch = nullptr;
-    const size_t per = (size_t)nblk * GPC_BLK * GPC_BLK + (size_t)n * n;
-    if (cudaMalloc(&scratch, per * batch * sizeof(double)) != cudaSuccess) return set_err(GPC_E_WORKSPACE, "gpc_dbg_linalg: cudaMalloc failed%s");
-    k_dbg_linalg<<<batch, GPC_THREADS, smem_bytes(), (cudaStream_t)stream>>>(op, n, nrhs, A, B, status, scratch);
+    if (op < 0 || op > 4 || batch < 1 || n < 1 || !A || !status || !scratch)
+        return set_err(GPC_E_ARG, "gpc_dbg_linalg: bad argument%s");
+    if (scratch_bytes < gpc_dbg_linalg_scratch_bytes(batch, n))
+        return set_err(GPC_E_WORKSPACE, "gpc_dbg_linalg: scratch too small%s");
+    k_dbg_linalg<<<batch, GPC_THREADS, smem_bytes(), (cudaStream_t)stream>>>(op, n, nrhs, A, B, status, (double*)scratch);
     ++g_launches;
-    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
-    cudaFree(scratch);
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_err(GPC_E_LAUNCH, "gpc_dbg_linalg: %s", cudaGetErrorString(e));
     return 0;
 }
 
-void gpc_dbg_set_trace(double* buf, int32_t cap, int32_t gene, int32_t model) {
-    g_trace = buf; g_trace_cap = cap; g_trace_gene = gene; g_trace_model = model;
-}
-
-int64_t gpc_launch_count(void) { return g_launches; }
+int64_t gpc_launch_count(void) { return g_launches.load(); }
 const char* gpc_last_error_string(void) { return g_err; }
 const char* gpc_version(void) { return "gpcounts_b200 0.1 (sm_100a)"; }
 

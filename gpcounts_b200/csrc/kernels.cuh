@@ -159,6 +159,22 @@ __device__ bool fit_one(const FitArgs& a, int g, int k, double prev_alpha, const
             ls = t[0]; var = t[1]; alpha = t[2]; km = t[3];
         }
         if (md.kernel == GPC_CONST) ls = 1.0;
+        {
+            // gpflow refuses a Parameter whose unconstrained value is not finite (e.g. variance 0 of an all-zero gene:
+            // softplus^-1(0) = -inf) with tf.errors.InvalidArgumentError, which fit_GP answers like a failed Cholesky
+            // factorisation: random restart (:547-556).  CTA-uniform values.
+            const bool use_al = md.lik == GPC_NB || md.lik == GPC_ZINB || md.lik == GPC_GAUSS;
+            const double al_eff = md.lik == GPC_GAUSS ? alpha - GPC_GAUSS_VAR_LOWER : alpha;
+            bool finite0 = isfinite(softplus_inv_d(var)) && isfinite(softplus_inv_d(ls));
+            if (use_al) finite0 = finite0 && isfinite(softplus_inv_d(al_eff));
+            if (md.lik == GPC_ZINB) finite0 = finite0 && isfinite(softplus_inv_d(km));
+            if (!finite0) {
+                r.task = TASK_CHOL; r.nit = 0; r.nfev = 0; r.f = NAN; r.gnorm = NAN; r.eval_cycles = 0;
+                ok = false;
+                if (attempt >= max_restart) break;
+                continue;
+            }
+        }
         // theta0: hyper-parameters through softplus^-1, q_mu = 0, q_sqrt = I
         for (int i = tid; i < md.P; i += GPC_THREADS) ws.x[i] = 0.0;
         __syncthreads();
@@ -166,7 +182,7 @@ __device__ bool fit_one(const FitArgs& a, int g, int k, double prev_alpha, const
             ws.x[0] = softplus_inv_d(var);
             ws.x[1] = softplus_inv_d(ls);
             ws.x[2] = softplus_inv_d(md.lik == GPC_GAUSS ? alpha - GPC_GAUSS_VAR_LOWER : alpha);
-            ws.x[3] = softplus_inv_d(km);
+            ws.x[3] = md.lik == GPC_ZINB ? softplus_inv_d(km) : (km > 0.0 && isfinite(softplus_inv_d(km)) ? softplus_inv_d(km) : 0.0);
         }
         for (int i = tid; i < md.Mv; i += GPC_THREADS) ws.x[GPC_NHYP + md.Mv + tri_index(i, i)] = 1.0;
         __syncthreads();

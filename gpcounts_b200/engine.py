@@ -15,14 +15,35 @@ KERNEL = {"RBF": L.GPC_RBF, "CONST": L.GPC_CONST, "BRANCH": L.GPC_BRANCH}
 LIK = {"NB": L.GPC_NB, "ZINB": L.GPC_ZINB, "POISSON": L.GPC_POISSON, "GAUSS": L.GPC_GAUSS}
 
 
+_pinned = {"buf": None, "event": None}
+
+
+def _pinned_stage(nbytes):
+    """Grow-only pinned staging buffer, reused across calls (a fresh cudaHostAlloc per call costs milliseconds);
+    the previous asynchronous copy out of it is awaited before it is overwritten."""
+    if _pinned["event"] is not None:
+        _pinned["event"].synchronize()
+        _pinned["event"] = None
+    buf = _pinned["buf"]
+    if buf is None or buf.numel() < nbytes:
+        _pinned["buf"] = buf = torch.empty(int(nbytes), dtype=torch.uint8).pin_memory()
+    return buf
+
+
 def _dev_f64(a, device):
     if a is None:
         return None
     if isinstance(a, np.ndarray):
-        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
-        if torch.device(device).type == "cuda" and t.numel() >= (1 << 16):
-            t = t.pin_memory()                      # H2D from pinned host memory
-        return t.to(device, non_blocking=True)
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if torch.device(device).type == "cuda" and a.size >= (1 << 16):
+            stage = _pinned_stage(a.nbytes)[: a.nbytes].view(torch.float64).view(a.shape)
+            stage.copy_(torch.from_numpy(a))        # H2D from pinned host memory
+            out = stage.to(device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(device))
+            _pinned["event"] = ev
+            return out
+        return torch.from_numpy(a).to(device)
     t = torch.as_tensor(a, dtype=torch.float64)
     return t.to(device).contiguous()
 
@@ -176,9 +197,11 @@ def dbg_linalg(op, A, B=None, nrhs=0):
     dev = A.device
     batch, n = A.shape[0], A.shape[1]
     status = torch.empty(batch, dtype=torch.int32, device=dev)
+    scratch = torch.empty(int(lib.gpc_dbg_linalg_scratch_bytes(batch, n)), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         L.check(lib.gpc_dbg_linalg(op, batch, n, nrhs, A.data_ptr(), B.data_ptr() if B is not None else None,
-                                   status.data_ptr(), _stream_ptr(dev)))
+                                   status.data_ptr(), scratch.data_ptr(), scratch.numel(), _stream_ptr(dev)))
+        torch.cuda.synchronize(dev)         # the scratch buffer must outlive the (stream-ordered) kernel
     return status
 
 

@@ -97,7 +97,10 @@ def inducing_sets(X, M, ls0, with_restarts=True):
 def qvalue(pv, pi0=None):
     """Storey q-values (reference: GPcounts_Module.py:1008-1063, SciPy aliases replaced by NumPy)."""
     pv = np.asarray(pv, dtype=np.float64)
-    assert pv.min() >= 0 and pv.max() <= 1, "p-values should be between 0 and 1"
+    # the reference receives a pandas Series, whose min() / max() skip the NaN p-values of failed fits (:455-457);
+    # NaN rows sort last, keep m = len(pv) and come out as NaN q-values, exactly as there
+    if np.isfinite(pv).any():
+        assert np.nanmin(pv) >= 0 and np.nanmax(pv) <= 1, "p-values should be between 0 and 1"
     shape = pv.shape
     pv = pv.ravel()
     m = float(len(pv))

@@ -9,8 +9,10 @@
  * SciPy L-BFGS-B loop (see INTEGRATION.md for the stub).
  *
  * Conventions: plain C, device pointers + sizes + an opaque CUDA stream handle (cudaStream_t passed as
- * void*); the caller owns every buffer including the workspace; the library keeps no state between
- * calls except the last error string.  Every function returns 0 on success and a negative GPC_E_* code
+ * void*); the caller owns every buffer including the workspace.  State kept by the library between calls: the
+ * thread-local last-error string, a mutex-guarded per-device "constants uploaded" latch (Gauss-Hermite table) and an
+ * atomic launch counter - nothing else (no environment variables, no allocations, no host synchronisation).
+ * Every function returns 0 on success and a negative GPC_E_* code
  * on argument / launch errors.  Per-gene numerical failures are not errors: they are reported in the
  * per-(gene, model) statistics rows exactly like the reference reports them (NaN log-likelihood).
  *
@@ -95,6 +97,12 @@ typedef struct gpc_opt {
     int32_t maxls;         /* 20 (SciPy default)                      */
     double ftol;           /* 2.220446049250313e-09 (SciPy default)   */
     double gtol;           /* 1e-5 (SciPy default)                    */
+    /* debug / measurement knobs (gpc_default_opt leaves them off) */
+    int32_t variant;       /* -1: the library picks the kernel instantiation; >= 0 forces one (A/B measurements) */
+    int32_t trace_cap;     /* capacity of `trace` in records of 8 doubles                                        */
+    int32_t trace_gene;    /* record (loss, step, slope, max|g|, theta[0..3]) of every evaluation of attempt 0   */
+    int32_t trace_model;   /*   of this (gene, model) ...                                                        */
+    double* trace;         /*   ... into this device buffer; NULL = off                                          */
 } gpc_opt_t;
 
 /* Default optimiser settings = gpflow.optimizers.Scipy / SciPy L-BFGS-B defaults with maxiter=5000. */
@@ -150,11 +158,9 @@ int gpc_fit(const gpc_model_t* models, int32_t n_models, int32_t chain, const gp
  *   op 4: chol_bwd   B (n x n, lower = Lbar) <- L^-T Phi(L^T Lbar) L^-1   (unsymmetrised)
  */
 int gpc_dbg_linalg(int32_t op, int32_t batch, int32_t n, int32_t nrhs, double* A, double* B, int32_t* status,
-                   void* stream);
-
-/* Debug hook: record (loss, step, slope, max|g|, theta[0..3]) of every evaluation of attempt 0 of (gene, model)
- * during subsequent gpc_fit calls into buf (device, cap x 8 doubles); buf = NULL switches it off. */
-void gpc_dbg_set_trace(double* buf, int32_t cap, int32_t gene, int32_t model);
+                   void* scratch, size_t scratch_bytes, void* stream);
+/* Bytes of caller-provided device scratch gpc_dbg_linalg needs (stream-ordered, no allocation inside the library). */
+size_t gpc_dbg_linalg_scratch_bytes(int32_t batch, int32_t n);
 
 /* Number of kernel launches issued by this library since load (bench.py `gpu_launches`). */
 int64_t gpc_launch_count(void);

@@ -149,6 +149,11 @@ class OracleFit:
             theta0 = gm.initial_theta(spec, var, ls, alpha, km)
             out = FitResult(spec=spec, restarts=count_fix)
             try:
+                # gpflow.Parameter rejects a non-finite unconstrained value (variance 0 of an all-zero gene gives
+                # softplus^-1(0) = -inf) with tf.errors.InvalidArgumentError, caught at :547 like a Cholesky failure
+                used = [True, kernel != "CONST", lik in ("NB", "ZINB", "GAUSS"), lik == "ZINB"]
+                if not all(np.isfinite(theta0[i]) for i in range(4) if used[i]):
+                    raise CholeskyFailure("non-finite unconstrained initial value")
                 res, theta = minimize_lbfgsb(spec, theta0, y, scale, self.lbfgs_options)
                 out.nit, out.nfev, out.message = res.nit, res.nfev, str(res.message)
                 if res.success:                                                          # :699

@@ -35,7 +35,8 @@ def test_struct_layout_matches_header(lib):
     from gpcounts_b200 import _lib
     # 10 int32 + 2 double + 4 pointers, natural alignment
     assert ctypes.sizeof(_lib.gpc_model_t) == 10 * 4 + 2 * 8 + 4 * 8
-    assert ctypes.sizeof(_lib.gpc_opt_t) == 4 * 4 + 2 * 8
+    # 4 int32 + 2 double + 4 int32 (variant, trace_cap, trace_gene, trace_model) + 1 pointer
+    assert ctypes.sizeof(_lib.gpc_opt_t) == 4 * 4 + 2 * 8 + 4 * 4 + 8
 
 
 def test_defaults_and_param_count(lib):
@@ -44,6 +45,7 @@ def test_defaults_and_param_count(lib):
     lib.gpc_default_opt(ctypes.byref(o))
     assert (o.m, o.maxiter, o.maxfun, o.maxls) == (10, 5000, 15000, 20)
     assert o.ftol == 2.220446049250313e-09 and o.gtol == 1e-5
+    assert o.variant == -1 and not o.trace and o.trace_cap == 0
     m = _lib.gpc_model_t()
     m.kind, m.N, m.M = _lib.GPC_SVGP, 1000, 64
     assert lib.gpc_param_count(ctypes.byref(m)) == 4 + 64 + 64 * 65 // 2
@@ -60,6 +62,13 @@ def test_argument_errors_are_reported_without_a_gpu(lib):
     lib.gpc_default_opt(ctypes.byref(o))
     nbytes = lib.gpc_workspace_bytes(ctypes.byref(m), 1, ctypes.byref(o), 4)
     assert nbytes > 0
+
+
+def test_library_reads_no_environment_and_keeps_no_debug_globals():
+    """trace / variant overrides travel in gpc_opt_t, not in globals or environment variables."""
+    for f in os.listdir(os.path.join(ROOT, "gpcounts_b200", "csrc")):
+        txt = open(os.path.join(ROOT, "gpcounts_b200", "csrc", f)).read()
+        assert "getenv" not in txt and "cudaMalloc(" not in txt and "cudaStreamSynchronize" not in txt, f
 
 
 def test_no_cpu_fallback():

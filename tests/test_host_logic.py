@@ -128,3 +128,24 @@ def test_per_gene_inducing_selection_matches_host_recurrence():
         np.random.seed(0)
         Zh = host.greedy_conditional_variance(X, 12, ls, var[g])
         assert np.array_equal(np.sort(Z[g].ravel()), np.sort(Zh.ravel()))
+
+
+def test_qvalue_with_nan_rows_follows_the_reference():
+    """A failed fit gives a NaN LLR (:455-457); the reference's qvalue receives a pandas Series whose min()/max() skip
+    NaN, keeps m = len(pv), sorts NaN last and returns NaN only for those rows."""
+    from gpcounts_b200 import Fit_GPcounts, host
+    llr = np.array([12.0, 0.3, np.nan, 3.1, 0.0])
+    df = pd.DataFrame({"log_likelihood_ratio": llr}, index=list("abcde"))
+    gp = Fit_GPcounts.__new__(Fit_GPcounts)
+    out = Fit_GPcounts.calculate_FDR(gp, df)
+    p = out["p_value"].values
+    assert np.isnan(p[2]) and np.isnan(out["q_value"].values[2])
+    ok = ~np.isnan(p)
+    order = np.argsort(p[ok])
+    ps = p[ok][order]
+    q = np.zeros(4)
+    q[-1] = 5.0 * ps[-1] / 4.0            # m = 5 (NaN counted), rank 4 is the last finite one
+    for i in range(2, -1, -1):
+        q[i] = min(5.0 * ps[i] / (i + 1.0), q[i + 1])
+    assert np.allclose(out["q_value"].values[ok][order], q)
+    assert np.isnan(host.qvalue(np.array([np.nan, np.nan]))).all()

@@ -1,4 +1,4 @@
-"""Evaluation trace of one (gene, model) fit of a golden fixture (debug hook gpc_dbg_set_trace):
+"""Evaluation trace of one (gene, model) fit of a golden fixture (debug fields of gpc_opt_t: trace, trace_cap, trace_gene, trace_model):
 
     python tools/trace_gene.py one_sample_sparse_nb 0 0
 
@@ -15,9 +15,8 @@ gp = Fit_GPcounts(pd.DataFrame(X, index=cells), pd.DataFrame(Y, index=["g%d" % i
 lib = _lib.load()
 cap = 4000
 buf = torch.zeros(cap * 8, dtype=torch.float64, device="cuda")
-lib.gpc_dbg_set_trace(C.c_void_p(buf.data_ptr()), cap, gene, model)
+gp.optimizer_options = dict(trace=buf.data_ptr(), trace_cap=cap, trace_gene=gene, trace_model=model)
 df = gp.One_sample_test(str(fx["lik"]))
-lib.gpc_dbg_set_trace(None, 0, -1, -1)
 torch.cuda.synchronize()
 print(df.iloc[gene].values, "oracle", fx["ll"][gene])
 st = gp.fit_stats
