@@ -342,7 +342,7 @@ class Fit_GPcounts(object):
             return self._run_branching_stage(genes_index)
         column_name = self._column_names(models_number)
         genes_index = list(genes_index)
-        Y = np.asarray(self.Y, dtype=np.float64)
+        Y = np.ascontiguousarray(self.Y, dtype=np.float64)
         Yfit = np.log(Y + 1) if (lik_name == "Gaussian" and self.transform) else Y      # :650-652
         X = self.X
         if models_number == 1:
@@ -407,7 +407,7 @@ class Fit_GPcounts(object):
     def _run_branching_stage(self, genes_index):
         """Free fit (fix=False): BranchKernel(RBF(1, 1), xp) for every gene; ``self.model`` = last gene (:262-265)."""
         genes_index = list(genes_index)
-        Y = np.asarray(self.Y, dtype=np.float64)
+        Y = np.ascontiguousarray(self.Y, dtype=np.float64)
         Yfit = np.log(Y + 1) if (self.lik_name == "Gaussian" and self.transform) else Y
         models = [self._make_model("BRANCH", self.X, xp=float(self.xp))]
         hyp0 = self._hyp0(Y, self.X, kernel="BRANCH")[:, None, :]
@@ -425,7 +425,7 @@ class Fit_GPcounts(object):
         self.fix = True
         X = self.X
         g_last = self.D - 1                 # the reference keeps only the last gene's models (:289-290)
-        Y = np.asarray(self.Y, dtype=np.float64)
+        Y = np.ascontiguousarray(self.Y, dtype=np.float64)
         Yfit = np.log(Y + 1) if (lik_name == "Gaussian" and self.transform) else Y
         fixed = (float(self.branching_kernel_var), float(self.branching_kernel_ls))
         models, Xs = [], []

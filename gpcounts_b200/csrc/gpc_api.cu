@@ -239,6 +239,14 @@ int gpc_dbg_linalg(int32_t op, int32_t batch, int32_t n, int32_t nrhs, double* A
 }
 
 int64_t gpc_launch_count(void) { return g_launches.load(); }
+
+#ifdef GPC_PHASE_PROF
+// profiling build only (tools/phase_prof.py): read and reset the phase timers of the fused evaluator of one instantiation
+int gpc_dbg_phase_prof(int variant, unsigned long long* out16) {
+    if (ensure_init() != 0 || variant < 0 || variant > 2 || !g_ops[variant].read_prof) return -1;
+    return g_ops[variant].read_prof(out16);
+}
+#endif
 const char* gpc_last_error_string(void) { return g_err; }
 const char* gpc_version(void) { return "gpcounts_b200 0.1 (sm_100a)"; }
 

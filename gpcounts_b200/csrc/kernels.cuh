@@ -25,6 +25,7 @@ struct VariantOps {
     int (*occupancy)();
     cudaError_t (*launch_fit)(const void* fit_args, int grid, cudaStream_t s);
     cudaError_t (*launch_eval)(const void* eval_args, int grid, cudaStream_t s);
+    int (*read_prof)(unsigned long long* out16);   // profiling build only (GPC_PHASE_PROF), else nullptr
 };
 
 namespace {   // everything below is private to the including translation unit
@@ -326,6 +327,16 @@ static cudaError_t GPC_KNAME(v_launch_eval)(const void* a, int grid, cudaStream_
     return cudaGetLastError();
 }
 
+#if defined(GPC_PHASE_PROF) && !defined(GPC_DENSE_ONLY)
+static int GPC_KNAME(v_read_prof)(unsigned long long* out16) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out16, g_phase_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_phase_prof, z, sizeof(z));
+    return 0;
+}
+#endif
+
 }  // anonymous namespace
 
 // exported (C++ linkage) accessor of this instantiation
@@ -336,5 +347,9 @@ VariantOps GPC_KNAME(gpc_variant_ops)() {
     o.occupancy = GPC_KNAME(v_occupancy);
     o.launch_fit = GPC_KNAME(v_launch_fit);
     o.launch_eval = GPC_KNAME(v_launch_eval);
+    o.read_prof = nullptr;
+#if defined(GPC_PHASE_PROF) && !defined(GPC_DENSE_ONLY)
+    o.read_prof = GPC_KNAME(v_read_prof);
+#endif
     return o;
 }

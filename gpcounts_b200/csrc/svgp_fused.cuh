@@ -26,6 +26,19 @@
 
 static_assert(FZ_WPR == 1, "the fused evaluator is written for 8 warps (256 threads)");
 
+// Phase timers (tools/phase_prof.py builds a separate profiling library with -DGPC_PHASE_PROF; the product build has none):
+// thread 0 accumulates SM-clock deltas between phase boundaries of every evaluation into g_phase_prof.
+#ifdef GPC_PHASE_PROF
+__device__ unsigned long long g_phase_prof[16];
+#define PROF_DECL long long prof_t = clock64(); long long prof_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define PROF_MARK(k) do { const long long t_ = clock64(); prof_acc[k] += t_ - prof_t; prof_t = t_; } while (0)
+#define PROF_FLUSH do { if (threadIdx.x == 0) { for (int q_ = 0; q_ < 10; ++q_) atomicAdd(&g_phase_prof[q_], (unsigned long long)prof_acc[q_]); atomicAdd(&g_phase_prof[15], 1ull); } } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(k)
+#define PROF_FLUSH
+#endif
+
 struct FusedSmem {
     double T0[FZ_MAT];              // Kuf tile            (end phase: Lq)
     double T1[FZ_MAT];              // A tile              (setup: Lq; end phase: H / Lm-bar / T)
@@ -284,6 +297,7 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
     // (instead of trusting the generic `fs` argument) lets the compiler emit shared-window loads and stores even when
     // this function is reached through a function pointer (plain ABI, no interprocedural address-space inference)
     fs = reinterpret_cast<FusedSmem*>(g_smem);
+    PROF_DECL;
     const int N = md.N, M = md.M, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nrb = (M + 7) >> 3, Mp = nrb * 8;          // 8-row blocks in use
     if (tid == 0) {
@@ -339,8 +353,11 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
                 make_double2(acc[ct][0] - (i == j ? 1.0 : 0.0), acc[ct][1] - (i == j + 1 ? 1.0 : 0.0));
         }
     }
+    PROF_MARK(0);
     if (!fz_chol(fs->T2, M)) return GPC_ST_CHOL;
+    PROF_MARK(1);
     fz_tri_inverse(fs->T2, M, fs->Linv);
+    PROF_MARK(2);
     if (need_kg) {
         for (int idx = tid; idx < 64 * 64; idx += GPC_THREADS) {   // keep Lm for the end phase
             const int i = idx >> 6, j = idx & 63;
@@ -387,6 +404,7 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
         }
     }
     const int ar = lane >> 2, ac = 2 * (lane & 3);
+    PROF_MARK(3);
     for (int n0 = 0; n0 < N; n0 += 64) {
         const int nt = min(64, N - n0);
         __syncthreads();
@@ -426,6 +444,7 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
             }
         }
         __syncthreads();
+        PROF_MARK(4);
         double acc[FZ_TPH][2], acc2[FZ_TPH][2];
         // ---- A = Linv * Kuf (k <= row) -> T1 --------------------------------------------------------------------
         if (active) {
@@ -436,6 +455,7 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
             accT_store<FZ_TPH>(acc2, fs->T1, rB, ctB);
         }
         __syncthreads();
+        PROF_MARK(5);
         // ---- C = W * A (full k-range) -> T2 ------------------------------------------------------------------------
         if (active) {
             accT_zero<FZ_TPH>(acc); accT_zero<FZ_TPH>(acc2);
@@ -445,6 +465,7 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
             accT_store<FZ_TPH>(acc2, fs->T2, rB, ctB);
         }
         __syncthreads();
+        PROF_MARK(6);
         // ---- per-column statistics + quadrature: FZ_LPC adjacent lanes per column ---------------------------------
         //   fmean = a . q_mu,  fvar = kdiag + a . (W a)
         {
@@ -500,6 +521,7 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
             }
         }
         __syncthreads();
+        PROF_MARK(7);
         // ---- gq += A gm;  S = u gm^T + (Linv^T C) diag(2 gv) in registers -> <S o Kuf, R^2> ---------------------------
         if (active) {
             if (need_s) {
@@ -561,6 +583,7 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
                 }
             }
         }
+        PROF_MARK(8);
     }
     __syncthreads();
     // ---- end phase ------------------------------------------------------------------------------------------------
@@ -704,6 +727,8 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
     store_hyper_grad(md, h, gvar, gls, acc6[1], acc6[2], grad);
     *f_out = acc6[0] - kl;
     __syncthreads();
+    PROF_MARK(9);
+    PROF_FLUSH;
     return GPC_ST_OK;
 }
 

@@ -20,6 +20,10 @@ def default_lengthscale(X):
 
 def default_variance(Y, lik_name, transform):
     """Per-gene initial kernel variance (reference: GPcounts_Module.py:734-738), Y is (D, N)."""
+    # The reference reduces one gene at a time over a contiguous copy of its row (:421-422, :738): NumPy's pairwise
+    # summation.  A (D, N) array taken from a DataFrame is Fortran-ordered, and reducing it along axis 1 sums in a
+    # different order (1-ulp differences that decide where a creeping L-BFGS-B run stops) - so force row-major here.
+    Y = np.ascontiguousarray(Y, dtype=np.float64)
     if lik_name == "Gaussian" and not transform:
         return np.mean(Y + 1 ** 2, axis=1)            # operator-precedence quirk of the reference kept (:736)
     with np.errstate(divide="ignore", invalid="ignore"):

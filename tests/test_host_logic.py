@@ -149,3 +149,16 @@ def test_qvalue_with_nan_rows_follows_the_reference():
         q[i] = min(5.0 * ps[i] / (i + 1.0), q[i + 1])
     assert np.allclose(out["q_value"].values[ok][order], q)
     assert np.isnan(host.qvalue(np.array([np.nan, np.nan]))).all()
+
+
+def test_default_variance_is_independent_of_batch_shape_and_memory_order():
+    """`DataFrame.values` is Fortran-ordered; the per-gene initial variance must still be the reference's per-gene
+    contiguous reduction (:421-422, :738), bit for bit, whatever the batch a gene arrives in."""
+    from gpcounts_b200 import host
+    rng = np.random.default_rng(0)
+    Y = rng.poisson(7.0, (101, 20)).astype(float)
+    ref = np.array([np.mean(np.log(Y[g].astype(float).reshape([-1, 1]) + 1) ** 2) for g in range(101)])
+    Yf = pd.DataFrame(Y).values if False else np.asfortranarray(Y)
+    assert np.array_equal(host.default_variance(Yf, "Negative_binomial", True), ref)
+    assert np.array_equal(host.default_variance(Y, "Negative_binomial", True), ref)
+    assert host.default_variance(Yf[5:6], "Negative_binomial", True)[0] == ref[5]
