@@ -14,6 +14,7 @@
 // that the triangular k-ranges are warp-uniform, row blocks paired (w, nrb-1-w) so that every warp does the same work.
 #pragma once
 #include "model.cuh"
+#include "fastmath.cuh"
 
 #define FZ_LD 68                    // leading dimension of every smem matrix (== 4 mod 16: conflict-free DMMA fragments)
 #define FZ_MAT (64 * FZ_LD)         // doubles per 64 x 64 smem matrix
@@ -50,6 +51,8 @@ struct FusedSmem {
     double gq[2 * FZ_WPR][64];      // A g_m accumulators, one per column group of a tile (deterministic sums)
     double col[8][64];              // per column: -, -, gm, -, y, scale, 2*gv; [7] = u = Lm^-T q_mu (per row)
     double red[64];
+    double red2[80];                // reduction scratch for up to 10 sums (cta_sum_n<K> uses K x 8 doubles)
+    int chol_ok;                    // blocked Cholesky: all pivots positive so far
     double Zs[64 * 2];              // inducing inputs (d <= 2)
     double Xs[64 * 2];              // inputs of the current column tile
     KernParams kp;                  // per-evaluation constants live here rather than in registers: the evaluator
@@ -147,84 +150,76 @@ __device__ __forceinline__ void acc_store(const double (&acc)[8][2], double* C, 
             *reinterpret_cast<double2*>(&C[(r0 + ar) * FZ_LD + ct * 8 + ac]) = make_double2(acc[ct][0], acc[ct][1]);
 }
 
-// Cholesky of the n x n SPD matrix in smem D (ld FZ_LD, lower part used), result in the lower triangle of D.
-// Left-looking, four lanes per row: lane q of row i keeps the entries l_ik with k = q (mod 4) in registers, so an
-// element is produced by one dot product (no read-modify-write of the trailing matrix).  Every row group recomputes
-// the pivot d_jj = a_jj - sum_k l_jk^2 from row j in shared memory, which leaves ONE barrier per column.
-__device__ bool fz_chol(double* D, int n) {
-    const int tid = threadIdx.x;
-    const int i = tid >> 2, q = tid & 3;          // row, lane within the row group (rows >= 64 idle when GPC_THREADS > 256)
-    double lk[16];
+// x^-1/2 without a slow-path branch: hardware seed (MUFU.RSQ64H) + two third-order Newton steps.
+__device__ __forceinline__ double gpc_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
 #pragma unroll
-    for (int t = 0; t < 16; ++t) lk[t] = 0.0;
-    bool ok = true;
-    double lii = 0.0;
-    for (int j = 0; j < n; ++j) {
-        __syncthreads();
-        // partial sums over k = q, q+4, ... < j of l_jk^2 (pivot) and l_ik l_jk (this row)
-        // four interleaved partial sums per dot product: the dependent FMA chain is 4 deep instead of 16
-        double pj4[4] = {0.0, 0.0, 0.0, 0.0}, pi4[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int t = 0; t < 16; ++t) {
-            const int k = q + 4 * t;
-            if (k < j) {
-                const double ljk = D[j * FZ_LD + k];
-                pj4[t & 3] = fma(ljk, ljk, pj4[t & 3]);
-                pi4[t & 3] = fma(lk[t], ljk, pi4[t & 3]);
-            }
-        }
-        double pj = (pj4[0] + pj4[1]) + (pj4[2] + pj4[3]), pi = (pi4[0] + pi4[1]) + (pi4[2] + pi4[3]);
-        pj += __shfl_xor_sync(0xffffffffu, pj, 1); pj += __shfl_xor_sync(0xffffffffu, pj, 2);
-        pi += __shfl_xor_sync(0xffffffffu, pi, 1); pi += __shfl_xor_sync(0xffffffffu, pi, 2);
-        const double djj = D[j * FZ_LD + j] - pj;
-        if (!(djj > 0.0)) { ok = false; break; }   // uniform: every thread evaluates the same pivot
-        const double ljj = sqrt(djj);
-        if (i < n && i >= j) {
-            const double lij = (i == j) ? ljj : (D[i * FZ_LD + j] - pi) / ljj;
-#pragma unroll
-            for (int t = 0; t < 16; ++t)
-                if (q + 4 * t == j) lk[t] = lij;
-            // the diagonal entry still holds a_jj, which slower warps read for this column's pivot: it is replaced
-            // by l_jj only after the loop
-            if (i == j) lii = lij;
-            else if (q == 0) D[i * FZ_LD + j] = lij;    // column j of row i is final
-        }
+    for (int it = 0; it < 2; ++it) {                       // third-order steps: 20 -> 60 -> 180 bits
+        const double e = fma(-x * y, y, 1.0);
+        y = fma(y * e, fma(0.375, e, 0.5), y);
     }
-    __syncthreads();
-    if (ok && q == 0 && i < n) D[i * FZ_LD + i] = lii;
-    __syncthreads();
-    return ok;
+    return y;
 }
 
-// X (smem, 64 x 64, ld FZ_LD) <- inverse of the lower-triangular n x n matrix L (smem), identity-padded to 64.
-__device__ void fz_tri_inverse(const double* L, int n, double* X) {
-    const int tid = threadIdx.x;
-    const int c = tid >> 2, q = tid & 3;
-    double xk[16];
-#pragma unroll
-    for (int t = 0; t < 16; ++t) xk[t] = 0.0;
-    for (int i = 0; i < 64; ++i) {
-        double xi;
-        if (i < n) {
-            double p4[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-            for (int t = 0; t < 16; ++t) {
-                const int kk = q + 4 * t;
-                if (kk < i) p4[t & 3] = fma(L[i * FZ_LD + kk], xk[t], p4[t & 3]);
-            }
-            double part = (p4[0] + p4[1]) + (p4[2] + p4[3]);
-            part += __shfl_xor_sync(0xffffffffu, part, 1);
-            part += __shfl_xor_sync(0xffffffffu, part, 2);
-            xi = (c < n && i >= c) ? ((i == c ? 1.0 : 0.0) - part) / L[i * FZ_LD + i] : 0.0;
-        } else {
-            xi = (i == c) ? 1.0 : 0.0;
-        }
-#pragma unroll
-        for (int t = 0; t < 16; ++t)
-            if (q + 4 * t == i) xk[t] = xi;
-        if (q == 0 && c < 64) X[i * FZ_LD + c] = xi;
+// One 8 x 8 tile product on the FP64 tensor pipe, operands in shared memory (ld FZ_LD):
+//   acc (8 x 8) += (+-) sum_{k < K} A[r][k] * Bop[k][c],   A -> A[0][0] of the 8 x K block (row-major),
+//   BT: B -> B[0][0] of an 8 x K block holding Bop^T ([c][k]);  else B -> Bop[0][0] of the K x 8 block.   K % 4 == 0.
+template <bool BT, bool NEG>
+__device__ __forceinline__ void tile_mma(double (&acc)[2], const double* __restrict__ A, const double* __restrict__ B, int K) {
+    const int lane = threadIdx.x & 31, ar = lane >> 2, ak = lane & 3;
+    for (int k0 = 0; k0 < K; k0 += 4) {
+        double a = A[ar * FZ_LD + k0 + ak];
+        if (NEG) a = -a;
+        const double b = BT ? B[ar * FZ_LD + k0 + ak] : B[(k0 + ak) * FZ_LD + ar];
+        dmma884(acc, a, b);
     }
-    __syncthreads();
+}
+
+// Cholesky factor and inverse of one 8 x 8 diagonal block by ONE warp, in registers: lane r (mod 8) holds row r, pivots
+// and column entries travel by shuffle.  Dblk (lower part read) is overwritten by L11 (zero above the diagonal), Iblk
+// receives L11^-1.  Returns false when a pivot is not positive (NaN included); warp-uniform.
+__device__ __forceinline__ bool fz_chol8(double* Dblk, double* Iblk) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, r = lane & 7;
+    double a[8], dinv[8], x[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a[c] = (c <= r) ? Dblk[r * FZ_LD + c] : 0.0;
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const double piv = __shfl_sync(FULL, a[j], j);
+        ok = ok && (piv > 0.0);
+        const double yv = gpc_rsqrt(piv);
+        double sq = piv * yv;
+        sq = fma(fma(-sq, sq, piv), 0.5 * yv, sq);          // sqrt(piv), one correction step
+        dinv[j] = yv;
+        a[j] = (r == j) ? sq : a[j] * yv;
+#pragma unroll
+        for (int c = j + 1; c < 8; ++c) {
+            const double lcj = __shfl_sync(FULL, a[j], c);
+            a[c] = (c <= r) ? fma(-a[j], lcj, a[c]) : 0.0;
+        }
+    }
+    // column r of the inverse by forward substitution; L[i][k] comes from lane i
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        double acc = (i == r) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) {
+            const double lik = __shfl_sync(FULL, a[k], i);
+            acc = fma(-lik, x[k], acc);
+        }
+        x[i] = (i >= r) ? acc * dinv[i] : 0.0;
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            Dblk[r * FZ_LD + c] = a[c];
+            Iblk[c * FZ_LD + r] = x[c];
+        }
+    }
+    return ok;
 }
 
 // Quadrature of one data point restricted to nodes [i0, i1): partial (ve, gm, gz, dalpha, dkm) sums.
@@ -286,6 +281,41 @@ __device__ __forceinline__ LikPart lik_nodes(const LikParams& lp, double fm, dou
     return o;
 }
 
+// NB nodes of one lane, vectorised: the lane's GPC_NGH / ISTEP nodes go through exp / log / reciprocal stage by stage
+// (fastmath.cuh), i.e. as independent dependency chains.  m = s e^F, so log m = F + log s: the node-independent term
+// y log s is added once per evaluation in the pre-pass.
+template <int ISTEP>
+__device__ __forceinline__ LikPart lik_nodes_nb(const LikParams& lp, double fm, double sd, double y, double s, int i0) {
+    constexpr int NK = GPC_NGH / ISTEP;
+    static_assert(NK * ISTEP == GPC_NGH, "nodes must split evenly over the lanes of a column");
+    LikPart o{0.0, 0.0, 0.0, 0.0, 0.0, false};
+    const double alpha = lp.alpha, k = lp.k, ia2 = k * k;
+    double F[NK], m[NK], t[NK], lt[NK], z[NK], w[NK];
+#pragma unroll
+    for (int q = 0; q < NK; ++q) {
+        z[q] = c_gh_z[i0 + q * ISTEP];
+        w[q] = c_gh_w[i0 + q * ISTEP];
+        F[q] = fma(sd, z[q], fm);
+    }
+    gpc_exp_v<NK>(F, m);
+#pragma unroll
+    for (int q = 0; q < NK; ++q) {
+        m[q] *= s;
+        t[q] = fma(m[q], alpha, 1.0);
+    }
+    gpc_log_v<NK>(t, lt);
+#pragma unroll
+    for (int q = 0; q < NK; ++q) {
+        const double it = gpc_rcp(t[q]);
+        const double mit = m[q] * it;
+        const double l = fma(y, (F[q] + lp.log_alpha) - lt[q], -k * lt[q]);
+        const double dl = (y - m[q]) * it;
+        const double dal = fma(lt[q], ia2, y * k) - (y + k) * mit;
+        o.ve = fma(w[q], l, o.ve); o.gm = fma(w[q], dl, o.gm); o.gz = fma(w[q] * z[q], dl, o.gz); o.da = fma(w[q], dal, o.da);
+    }
+    return o;
+}
+
 // ELBO + gradient of one SVGP gene-model, M <= 64.  Same contract as eval_svgp().
 // The body is force-inlined into its two users: the eval-only kernel (directly) and the out-of-line wrapper
 // eval_svgp_fused() that the fit kernel calls - ptxas register-allocates an out-of-line clone per kernel, and
@@ -336,9 +366,12 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
                 kv = kern_val(kp, r2, cross) + (i == j ? shift : 0.0);
             }
         }
+        if (i >= M && i == j) kv = 1.0;                    // identity padding: the blocked factorisation runs on whole 8-blocks
         fs->T1[i * FZ_LD + j] = lq;
         fs->T2[i * FZ_LD + j] = kv;
+        fs->Linv[i * FZ_LD + j] = (i == j) ? 1.0 : 0.0;
     }
+    if (tid == 0) fs->chol_ok = 1;
     __syncthreads();
     {
         // W[i][j] = sum_{k <= min(i, j)} Lq[i][k] Lq[j][k] - delta_ij   (row block `warp`, all column tiles)
@@ -354,9 +387,102 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
         }
     }
     PROF_MARK(0);
-    if (!fz_chol(fs->T2, M)) return GPC_ST_CHOL;
-    PROF_MARK(1);
-    fz_tri_inverse(fs->T2, M, fs->Linv);
+    double sum_ve = 0.0, sum_da = 0.0, sum_dk = 0.0, sum_gv = 0.0, sum_sk = 0.0, sum_skr = 0.0;
+    // Node-independent likelihood terms (lgamma / digamma of k + y, y log s) of all N points: three special-function calls
+    // per point.  They ride along with the factorisation below, on the seven warps that the 8 x 8 diagonal-block step
+    // (one warp, latency-bound) leaves idle: chunk c of the points is done during block step c.
+    auto prepass = [&](int c) {
+        if (md.lik != GPC_NB && md.lik != GPC_ZINB) return;
+        const double k2 = lp.k * lp.k;
+        const int per = (N + nrb - 1) / nrb, n1 = min(N, (c + 1) * per);
+        for (int n = c * per + (tid - 32); n < n1; n += GPC_THREADS - 32) {
+            const double yy = y[n];
+            if (md.lik == GPC_NB || yy != 0.0) {
+                const double xa[2] = {lp.k + yy, yy + 1.0};
+                double lg[2], dg[2];
+                gpc_lgamma_digamma_v<2>(xa, lg, dg);                         // branch-free, two chains (fastmath.cuh)
+                sum_ve += (lg[0] - lp.lgamma_k) - lg[1];
+                sum_da += -k2 * (dg[0] - lp.digamma_k);
+            }
+            if (md.lik == GPC_NB && scale) sum_ve += yy * gpc_log(scale[n]);  // log m = F + log s (see lik_nodes_nb)
+        }
+    };
+    // ---- Lm = chol(Kuu) in place in T2 and the inverses of its 8 x 8 diagonal blocks, right-looking with block size 8:
+    //   diagonal block: one warp in registers (fz_chol8);  panel L21 = A21 L11^-T and trailing update A22 -= L21 L21^T:
+    //   8 x 8 DMMA tiles over all warps.  Warp 0 updates the next diagonal block first and factors it while the other
+    //   warps finish the trailing tiles (look-ahead), so a block step costs one fz_chol8 + one panel + two barriers.
+    {
+        const int tar = lane >> 2, tac = 2 * (lane & 3);
+        if (warp == 0) {
+            const bool ok = fz_chol8(fs->T2, fs->Linv);
+            if (lane == 0 && !ok) fs->chol_ok = 0;
+        }
+        for (int kb = 0; kb < nrb; ++kb) {
+            __syncthreads();
+            {
+                const int rb = kb + 1 + warp;               // panel: one row block per warp
+                if (rb < nrb) {
+                    double acc[2] = {0.0, 0.0};
+                    tile_mma<true, false>(acc, &fs->T2[(rb * 8) * FZ_LD + kb * 8], &fs->Linv[(kb * 8) * FZ_LD + kb * 8], 8);
+                    __syncwarp();
+                    *reinterpret_cast<double2*>(&fs->T2[(rb * 8 + tar) * FZ_LD + kb * 8 + tac]) = make_double2(acc[0], acc[1]);
+                }
+            }
+            __syncthreads();
+            auto trail = [&](int rb, int cb) {
+                double* ct = &fs->T2[(rb * 8 + tar) * FZ_LD + cb * 8 + tac];
+                const double2 c0 = *reinterpret_cast<const double2*>(ct);
+                double acc[2] = {c0.x, c0.y};
+                tile_mma<true, true>(acc, &fs->T2[(rb * 8) * FZ_LD + kb * 8], &fs->T2[(cb * 8) * FZ_LD + kb * 8], 8);
+                *reinterpret_cast<double2*>(ct) = make_double2(acc[0], acc[1]);
+            };
+            if (warp == 0) {
+                if (kb + 1 < nrb) {
+                    trail(kb + 1, kb + 1);
+                    __syncwarp();
+                    const int o = ((kb + 1) * 8) * FZ_LD + (kb + 1) * 8;
+                    const bool ok = fz_chol8(fs->T2 + o, fs->Linv + o);
+                    if (lane == 0 && !ok) fs->chol_ok = 0;
+                }
+            } else {
+                int t = 0;
+                for (int rb = kb + 1; rb < nrb; ++rb) {
+                    for (int cb = kb + 1; cb <= rb; ++cb) {
+                        if (rb == kb + 1) continue;          // (kb+1, kb+1) belongs to warp 0
+                        if (t % 7 == warp - 1) trail(rb, cb);
+                        ++t;
+                    }
+                }
+                prepass(kb);
+            }
+        }
+        __syncthreads();
+        if (!fs->chol_ok) return GPC_ST_CHOL;
+        PROF_MARK(1);
+        // ---- Linv = Lm^-1 by recursive doubling over the blocks (8 -> 16 -> 32 -> 64): for a pair of diagonal blocks
+        //   [A 0; C B]^-1 = [A^-1 0; -B^-1 C A^-1  B^-1]:  T = C A^-1 (scratch T0), then -B^-1 T, 8 x 8 DMMA tiles.
+#pragma unroll
+        for (int lv = 0; lv < 3; ++lv) {
+            const int b = 8 << lv, nb8 = 1 << lv, tiles = (64 / (2 * b)) * nb8 * nb8;
+            for (int t = warp; t < tiles; t += FZ_NW) {
+                const int g = t >> (2 * lv), q = t & (nb8 * nb8 - 1), ti = q >> lv, tj = q & (nb8 - 1);
+                const int rowA = 2 * g * b, rowB = rowA + b;
+                double acc[2] = {0.0, 0.0};
+                tile_mma<false, false>(acc, &fs->T2[(rowB + ti * 8) * FZ_LD + rowA + tj * 8],
+                                       &fs->Linv[(rowA + tj * 8) * FZ_LD + rowA + tj * 8], b - tj * 8);
+                *reinterpret_cast<double2*>(&fs->T0[(rowB + ti * 8 + tar) * FZ_LD + rowA + tj * 8 + tac]) = make_double2(acc[0], acc[1]);
+            }
+            __syncthreads();
+            for (int t = warp; t < tiles; t += FZ_NW) {
+                const int g = t >> (2 * lv), q = t & (nb8 * nb8 - 1), ti = q >> lv, tj = q & (nb8 - 1);
+                const int rowA = 2 * g * b, rowB = rowA + b;
+                double acc[2] = {0.0, 0.0};
+                tile_mma<false, true>(acc, &fs->Linv[(rowB + ti * 8) * FZ_LD + rowB], &fs->T0[rowB * FZ_LD + rowA + tj * 8], ti * 8 + 8);
+                *reinterpret_cast<double2*>(&fs->Linv[(rowB + ti * 8 + tar) * FZ_LD + rowA + tj * 8 + tac]) = make_double2(acc[0], acc[1]);
+            }
+            __syncthreads();
+        }
+    }
     PROF_MARK(2);
     if (need_kg) {
         for (int idx = tid; idx < 64 * 64; idx += GPC_THREADS) {   // keep Lm for the end phase
@@ -390,19 +516,6 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
     double accHA[4][2], accHB[4][2];      // at most 4 tiles per segment for every nrb <= 8
     accT_zero<4>(accHA);
     accT_zero<4>(accHB);
-    double sum_ve = 0.0, sum_da = 0.0, sum_dk = 0.0, sum_gv = 0.0, sum_sk = 0.0, sum_skr = 0.0;
-    // node-independent likelihood terms (lgamma / digamma of k + y) of all N points in one converged pass: inside the
-    // tile loop they would run on 8 of a warp's 32 lanes, three serialised special-function calls per tile
-    if (md.lik == GPC_NB || md.lik == GPC_ZINB) {
-        const double k2 = lp.k * lp.k;
-        for (int n = tid; n < N; n += GPC_THREADS) {
-            const double yy = y[n];
-            if (md.lik == GPC_NB || yy != 0.0) {
-                sum_ve += (lgamma(lp.k + yy) - lp.lgamma_k) - lgamma(yy + 1.0);
-                sum_da += -k2 * (digamma_pos(lp.k + yy) - lp.digamma_k);
-            }
-        }
-    }
     const int ar = lane >> 2, ac = 2 * (lane & 3);
     PROF_MARK(3);
     for (int n0 = 0; n0 < N; n0 += 64) {
@@ -417,30 +530,40 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
         }
         __syncthreads();
         // ---- Kuf tile: thread owns column c = tid & 63, rows (tid >> 6) + FZ_LPC t ---------------------------------
+        // The FZ_RPT squared distances of a thread go through one vectorised exp (independent chains, fastmath.cuh);
+        // padded rows / columns (Zs, Xs are zero there) are computed too and masked on the way out.
         {
             const int c = tid & 63, ib = tid >> 6;
-            const double* xc = fs->Xs + c * dd;
             const bool cv = c < nt;
-            const double x0 = xc[0], x1 = dd > 1 ? xc[1] : 0.0;
-            const double ce = -0.5 * kp.inv_ls2;
-            const bool is_const = md.kernel == GPC_CONST;
+            const double var = kp.var;
+            if (md.kernel == GPC_CONST) {
 #pragma unroll
-            for (int t = 0; t < FZ_RPT; ++t) {
-                const int i = ib + FZ_LPC * t;
-                double kv = 0.0, kr = 0.0;
-                if (cv && i < M) {
-                    if (is_const) {
-                        kv = kp.var;
-                    } else {
-                        const double u = fs->Zs[i * dd] - x0;
-                        double r2 = u * u;
-                        if (dd > 1) { const double v = fs->Zs[i * dd + 1] - x1; r2 = fma(v, v, r2); }
-                        kv = kp.var * exp(ce * r2);
-                        kr = kv * r2;
-                    }
+                for (int t = 0; t < FZ_RPT; ++t) {
+                    const int i = ib + FZ_LPC * t;
+                    fs->T0[i * FZ_LD + c] = (cv && i < M) ? var : 0.0;
                 }
-                fs->T0[i * FZ_LD + c] = kv;
-                if (need_s) fs->T3[i * FZ_LD + c] = kr;      // Kuf o R^2, for d/d lengthscale
+            } else {
+                const double* xc = fs->Xs + c * dd;
+                const double x0 = xc[0], x1 = dd > 1 ? xc[1] : 0.0;
+                const double ce = -0.5 * kp.inv_ls2;
+                double r2[FZ_RPT], ev[FZ_RPT];
+#pragma unroll
+                for (int t = 0; t < FZ_RPT; ++t) {
+                    const int i = ib + FZ_LPC * t;
+                    const double u = fs->Zs[i * dd] - x0;
+                    double r = u * u;
+                    if (dd > 1) { const double v = fs->Zs[i * dd + 1] - x1; r = fma(v, v, r); }
+                    r2[t] = r;
+                    ev[t] = ce * r;
+                }
+                gpc_exp_v<FZ_RPT>(ev, ev);
+#pragma unroll
+                for (int t = 0; t < FZ_RPT; ++t) {
+                    const int i = ib + FZ_LPC * t;
+                    const double kv = (cv && i < M) ? var * ev[t] : 0.0;
+                    fs->T0[i * FZ_LD + c] = kv;
+                    if (need_s) fs->T3[i * FZ_LD + c] = kv * r2[t];      // Kuf o R^2, for d/d lengthscale
+                }
             }
         }
         __syncthreads();
@@ -498,7 +621,8 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
                     }
                 } else {
                     const double sd = sqrt(fv);
-                    const LikPart o = lik_nodes<FZ_LPC>(lp, fm, sd, yy, log(fs->col[5][c]), part);
+                    const LikPart o = (md.lik == GPC_NB) ? lik_nodes_nb<FZ_LPC>(lp, fm, sd, yy, fs->col[5][c], part)
+                                                         : lik_nodes<FZ_LPC>(lp, fm, sd, yy, 0.0, part);
                     ve = o.ve; gm = o.gm; gz = o.gz; da = o.da; dk = o.dk; poison = o.poison;
                 }
             }
@@ -587,13 +711,11 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
     }
     __syncthreads();
     // ---- end phase ------------------------------------------------------------------------------------------------
-    // H (symmetric) -> T1;  Lq -> T0
-    for (int idx = tid; idx < 64 * 64; idx += GPC_THREADS) {
+    // H (symmetric) -> T1 (every tile of the nrb x nrb block grid has exactly one owner, mirrors included);  Lq -> T0
+    for (int idx = tid; idx < Mp * 64; idx += GPC_THREADS) {
         const int i = idx >> 6, j = idx & 63;
-        fs->T1[i * FZ_LD + j] = 0.0;
         fs->T0[i * FZ_LD + j] = (i < M && j <= i) ? lq_packed[tri_index(i, j)] : 0.0;
     }
-    __syncthreads();
     if (active) {
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -639,24 +761,23 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
     }
     __syncthreads();
     double* glq = grad + GPC_NHYP + M;
-    for (int idx = tid; idx < M * M; idx += GPC_THREADS) {
-        const int i = idx / M, j = idx % M;
-        if (j <= i) {
+    double acc9[9] = {sum_ve, sum_da, sum_dk, sum_gv, sum_sk, sum_skr, 0.0, 0.0, 0.0};   // [6..8]: |q_mu|^2, |Lq|_F^2, sum log Lq_ii^2
+    for (int idx = tid; idx < Mp * 64; idx += GPC_THREADS) {
+        const int i = idx >> 6, j = idx & 63;
+        if (i < M && j <= i) {
             const double l = fs->T0[i * FZ_LD + j];
             glq[tri_index(i, j)] = fs->T2[i * FZ_LD + j] - (i == j ? l - 1.0 / l : l);
+            acc9[7] = fma(l, l, acc9[7]);
+            if (i == j) acc9[8] += log(l * l);
         }
     }
-    if (tid < M) grad[GPC_NHYP + tid] = (fs->gq[0][tid] + fs->gq[1][tid]) - fs->qmu[tid];
-    double acc6[6] = {sum_ve, sum_da, sum_dk, sum_gv, sum_sk, sum_skr};
-    cta_sum_n<6>(acc6, fs->red);
-    double klacc[3] = {0.0, 0.0, 0.0};
-    for (int idx = tid; idx < M * M; idx += GPC_THREADS) {
-        const int i = idx / M, j = idx % M;
-        if (j <= i) { const double l = fs->T0[i * FZ_LD + j]; klacc[1] = fma(l, l, klacc[1]); if (i == j) klacc[2] += log(l * l); }
+    if (tid < M) {
+        grad[GPC_NHYP + tid] = (fs->gq[0][tid] + fs->gq[1][tid]) - fs->qmu[tid];
+        acc9[6] = fs->qmu[tid] * fs->qmu[tid];
     }
-    if (tid < M) klacc[0] = fs->qmu[tid] * fs->qmu[tid];
-    cta_sum_n<3>(klacc, fs->red);
-    const double kl = 0.5 * (klacc[0] - (double)M + klacc[1] - klacc[2]);
+    cta_sum_n<9>(acc9, fs->red2);
+    const double* acc6 = acc9;
+    const double kl = 0.5 * (acc9[6] - (double)M + acc9[7] - acc9[8]);
     double gvar = 0.0, gls = 0.0;
     if (need_kg) {
         double acc[8][2];
@@ -710,13 +831,41 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
             acc_store(acc, fs->T3, r0, 0, 8);
         }
         __syncthreads();
+        // <Kbar, dKuu/dvar>, <Kbar, dKuu/dls>: the Gram entries are recomputed (vectorised exp, same thread -> entry map as
+        // the Kuf tiles: column j = tid & 63, rows (tid >> 6) + FZ_LPC t); RBF / Constant only on this path
         double a2[2] = {0.0, 0.0};
-        for (int idx = tid; idx < M * M; idx += GPC_THREADS) {
-            const int i = idx / M, j = idx % M;
-            bool cross;
-            const double r2 = kern_r2(kp, fs->Zs + i * dd, fs->Zs + j * dd, cross);
-            const double k0 = kern_val(kp, r2, cross);
-            kern_grad_acc(kp, fs->T3[i * FZ_LD + j], k0, r2, cross, a2[0], a2[1]);
+        {
+            const int j = tid & 63, ib = tid >> 6;
+            const bool jv = j < M;
+            if (md.kernel == GPC_CONST) {
+#pragma unroll
+                for (int t = 0; t < FZ_RPT; ++t) {
+                    const int i = ib + FZ_LPC * t;
+                    if (jv && i < M) a2[0] += fs->T3[i * FZ_LD + j];
+                }
+            } else {
+                const double z0 = fs->Zs[j * dd], z1 = dd > 1 ? fs->Zs[j * dd + 1] : 0.0;
+                const double ce = -0.5 * kp.inv_ls2;
+                double r2[FZ_RPT], ev[FZ_RPT];
+#pragma unroll
+                for (int t = 0; t < FZ_RPT; ++t) {
+                    const int i = ib + FZ_LPC * t;
+                    const double u = fs->Zs[i * dd] - z0;
+                    double r = u * u;
+                    if (dd > 1) { const double v = fs->Zs[i * dd + 1] - z1; r = fma(v, v, r); }
+                    r2[t] = r;
+                    ev[t] = ce * r;
+                }
+                gpc_exp_v<FZ_RPT>(ev, ev);
+#pragma unroll
+                for (int t = 0; t < FZ_RPT; ++t) {
+                    const int i = ib + FZ_LPC * t;
+                    const double gk = (jv && i < M) ? fs->T3[i * FZ_LD + j] * ev[t] : 0.0;     // Kbar_ij * K0_ij / var
+                    a2[0] += gk;
+                    a2[1] = fma(gk, r2[t], a2[1]);
+                }
+                a2[1] *= kp.var * kp.inv_ls3;
+            }
         }
         cta_sum_n<2>(a2, fs->red);
         // RBF / Constant: d Kuf / d var = Kuf / var, so <S, dKuf/dvar> = <Abar, A> / var
