@@ -49,6 +49,13 @@ class _NS:
         self.__dict__.update(kw)
 
 
+def _expand(a0, pending, D, genes_index):
+    """attempt0 table indexed by gene position in Y (what _run slices with the global gene indices)."""
+    full = np.zeros((D, a0.shape[1]), dtype=np.int32)
+    full[genes_index[pending]] = a0[pending]
+    return full
+
+
 class FittedModel:
     """Light stand-in for the gpflow model kept in ``Fit_GPcounts.model`` (attribute paths used by the
     reference and ``demo_notebooks/helper.py``: ``.kernel.variance``, ``.kernel.lengthscales``,
@@ -121,10 +128,8 @@ class Fit_GPcounts(object):
         self._z_cache = {}
         self.inducing_per_gene = False  # True: attempt 0 uses RobustGP points selected under each gene's own initial
                                         # variance, as the reference does; default: one shared set
-        if safe_mode:
-            raise NotImplementedError(
-                "safe_mode=True (stochastic posterior-predictive local-optimum checks, reference :558-565, "
-                ":808-857, :962-1006) is outside the B200 hot path; use safe_mode=False (the reference default).")
+        self._fitted = {}               # (test_name, lik_name) -> fitted parameter vectors on the device + model metadata
+        self.persist_models = False     # True: also write the fitted parameters under folder_name (reference :528-531)
         if (X is None) or (Y is None):
             print("TypeError: GPcounts() missing 2 required positional arguments: X and Y")
         else:
@@ -182,9 +187,95 @@ class Fit_GPcounts(object):
         raise NotImplementedError("Model_selection_test (Linear / Periodic kernels + BIC, reference :163-229) is "
                                   "outside the B200 hot path (SURVEY.md section 8f, rank 3).")
 
+    # ------------------------------------------------------------------------------------------ fitted models
+    _TEST_MODELS = {"Infer_trajectory": 1, "One_sample_test": 2, "Two_samples_test": 3}
+
+    def get_file_name(self, test_name=None, lik_name=None):
+        """Reference :709-723 names one TF checkpoint per (gene, model): <lik>_[sparse_][tst_]<gene>_model_<k>.  Here the
+        fitted parameter vectors of ALL genes and models of a test live in one file with the same prefix."""
+        import os
+        if not os.path.exists(self.folder_name):
+            os.mkdir(self.folder_name)
+        lik_name = lik_name or self.lik_name
+        n = self.models_number if test_name is None else self._TEST_MODELS.get(test_name, 1)
+        return self.folder_name + lik_name + "_" + ("sparse_" if self.sparse else "") + ("tst_" if n == 3 else "") + \
+            "models_%d.npz" % n
+
+    def _remember(self, test_name, models, names, stats, genes_index, Xs, Ys, kernel_names):
+        """Keep what load_predict_models needs: theta-hat of the local shard stays on the device, statistics on the host."""
+        key = (test_name, self.lik_name)
+        self._fitted[key] = dict(models=models, names=names, stats=np.asarray(stats), genes=[self.genes_name[g] for g in genes_index],
+                                 theta=self._last_theta, local_pos=np.asarray(self._last_local_pos), Xs=Xs, Ys=Ys,
+                                 kernels=kernel_names, Z=self.Z, sparse=self.sparse)
+        if self.persist_models and self._last_theta is not None:
+            pos = np.asarray(self._last_local_pos)
+            np.savez_compressed(self.get_file_name(test_name), genes=np.array(self._fitted[key]["genes"], dtype=object)[pos],
+                                theta=self._last_theta.cpu().numpy(), stats=np.asarray(stats)[pos], names=np.array(names),
+                                kernels=np.array(kernel_names), lik=self.lik_name, X=self.X,
+                                Z=self.Z if self.Z is not None else np.zeros(0), P=np.array([m.P for m in models]))
+
+    def _latent_at(self, model, theta, Xnew, Y=None, full_cov=True):
+        from . import engine
+        return engine.predict(model, theta, Xnew, Y=Y, full_cov=full_cov)
+
     def load_predict_models(self, genes_name, test_name, likelihood="Negative_binomial", predict=True):
-        raise NotImplementedError("load_predict_models (TF checkpoints + posterior-predictive sampling, reference "
-                                  ":859-960) is outside the B200 hot path (SURVEY.md section 8f, rank 2).")
+        """Reference :859-960: fitted models of the listed genes and, with ``predict``, their posterior predictive at 100
+        test inputs - ``predict_y`` for the Gaussian likelihood, the Monte-Carlo recipe of
+        ``samples_posterior_predictive_distribution`` otherwise (means: smoothed per-point averages, vars: the count samples).
+        The models come from the last run of ``test_name`` with this likelihood in this object (or, with
+        ``persist_models``, from the file written then)."""
+        from . import engine, predictive
+        self.Y = self.Y_copy
+        self.lik_name = likelihood
+        params = {"test_name": test_name, "likelihood": likelihood}
+        key = (test_name, likelihood)
+        if key not in self._fitted:
+            raise RuntimeError("no fitted models for %s / %s in this object: run the test first" % key)
+        fit = self._fitted[key]
+        models, K = fit["models"], len(fit["models"])
+        self.models_number = self._TEST_MODELS.get(test_name, 1)
+        X1 = self.X[:, :1] if self.X.shape[1] > 1 else self.X
+        xtest = np.linspace(np.min(self.X) - 0.1, np.max(self.X) + 0.1, 100)[:, None]          # :880
+        if self.X.shape[1] > 1:
+            xtest = self.X                                                                       # 2-D inputs: predict at the data
+        rows = [fit["genes"].index(g) for g in genes_name]
+        local = {int(p): i for i, p in enumerate(fit["local_pos"])}
+        missing = [genes_name[i] for i, r in enumerate(rows) if r not in local]
+        if missing:
+            raise RuntimeError("fitted parameters of %s live on another rank" % missing)
+        sel = [local[r] for r in rows]
+        genes_means, genes_vars, genes_models = [], [], []
+        per_model = []
+        for k, m in enumerate(models):
+            theta = fit["theta"][sel, k, :m.P].contiguous()
+            st = fit["stats"][rows, k]
+            Yk = fit["Ys"][k]
+            mean = var = None
+            if predict:
+                Yd = np.ascontiguousarray(Yk[rows]) if likelihood == "Gaussian" else None
+                mf, vf, cf = self._latent_at(m, theta, xtest, Y=Yd, full_cov=likelihood != "Gaussian")
+                if likelihood == "Gaussian":
+                    noise = torch.as_tensor(st[:, S_ALPHA], device=mf.device)[:, None]           # predict_y adds the noise variance
+                    mean, var = mf.cpu().numpy()[:, :, None], (vf + noise).cpu().numpy()[:, :, None]
+                else:
+                    dev = mf.device
+                    mean, var = predictive.posterior_predictive(
+                        likelihood, mf, cf, torch.as_tensor(st[:, S_ALPHA], device=dev), torch.as_tensor(st[:, S_KM], device=dev),
+                        branching=False, keep_samples=True)
+            per_model.append((theta, st, mean, var))
+        for i, g in enumerate(genes_name):
+            means, variances, mods = [], [], []
+            for k, m in enumerate(models):
+                theta, st, mean, var = per_model[k]
+                ok = not np.isnan(st[i, S_LL])
+                means.append(mean[i] if (predict and ok) else 0)
+                variances.append(var[i] if (predict and ok) else 0)
+                mods.append(FittedModel(st[i], theta[i].cpu().numpy(), fit["Xs"][k], fit["Ys"][k][rows[i]].reshape(-1, 1),
+                                        Z=fit["Z"] if fit["sparse"] else None, kernel=fit["kernels"][k], lik_name=likelihood)
+                            if ok else np.nan)
+            genes_means.append(means); genes_vars.append(variances); genes_models.append(mods)
+        params["means"], params["vars"], params["models"] = genes_means, genes_vars, genes_models
+        return params
 
     def kmean_algorithm_inducing_points(self, M=0):
         """Reference :382-390.  As in the reference the k-means centres are stored in ``self.Z`` but, because the
@@ -268,7 +359,7 @@ class Fit_GPcounts(object):
         return engine.Model(kind, kernel, lik, Xm, Z=Z, n_off=n_off, train=train, handoff_alpha=handoff, xp=xp,
                             restart=self._restart(Xm, kernel, fixed) if restarts else None, device=self._device())
 
-    def _run(self, models, Yfit, hyp0, chain, genes_index):
+    def _run(self, models, Yfit, hyp0, chain, genes_index, attempt0=None):
         """Shard genes over ranks (if torch.distributed is up), run gpc_fit, gather the statistics."""
         from . import engine, sharding
         dev = self._device()
@@ -291,8 +382,13 @@ class Fit_GPcounts(object):
                     if m.kernel == "RBF" and self.user_hyper_parameters[1] is None:
                         Xm = m.X.cpu().numpy()
                         m.Zgene = inducing.select_per_gene(Xm, m.M, float(hyp0[0, k, 1]), hyp0[gsel, k, 0], dev).contiguous()
+            opt = self._opt()
+            a0 = None
+            if attempt0 is not None:                                   # host-driven restarts of the safe mode
+                a0 = torch.as_tensor(np.ascontiguousarray(attempt0[gsel], dtype=np.int32), device=dev)
+                opt.attempt0 = a0.data_ptr()
             stats, theta = engine.fit(models, np.ascontiguousarray(Yfit[gsel]), scale, hyp0[gsel], chain=chain,
-                                      opt=self._opt(), return_theta=True)
+                                      opt=opt, return_theta=True)
         else:
             stats = torch.zeros(0, K, GPC_NSTAT, dtype=torch.float64, device=dev)
             theta = None
@@ -329,6 +425,103 @@ class Fit_GPcounts(object):
             self.model = FittedModel(row, theta, Xm, y, Z=self.Z if self.sparse else None, kernel=kernel, xp=xp,
                                      lik_name=self.lik_name)
 
+    # ------------------------------------------------------------------------------------------ safe mode
+    def _predictive_mean(self, model, theta, st, xtest, Yk):
+        """Mean of the posterior predictive at xtest for the rows of theta (reference :962-977)."""
+        from . import predictive
+        out = np.zeros((theta.shape[0], len(xtest)))
+        for c0 in range(0, theta.shape[0], 512):                       # bounded sampling buffers
+            sl = slice(c0, c0 + 512)
+            full = self.lik_name != "Gaussian"
+            mf, vf, cf = self._latent_at(model, theta[sl], xtest, Y=np.ascontiguousarray(Yk[sl]) if not full else None, full_cov=full)
+            if not full:
+                out[sl] = mf.cpu().numpy()                              # predict_y mean
+            else:
+                dev = mf.device
+                out[sl], _ = predictive.posterior_predictive(self.lik_name, mf, cf, torch.as_tensor(st[sl, S_ALPHA], device=dev),
+                                                             torch.as_tensor(st[sl, S_KM], device=dev), seed=c0)
+        return out
+
+    def _safe_fit(self, model, Yfit, hyp0, genes_index, constant_of_one_sample=False):
+        """``safe_mode=True`` for one model of the test (reference fit_GP :558-565, test_local_optima_case1 :962-1006,
+        positive log-likelihood in fit_model :518-525): after a successful fit whose restart count is below 5 the posterior
+        predictive mean is compared with the data range; a fit that fails the check (or has a positive log-likelihood) is
+        repeated from the next seeded random restart.  Host-driven: rounds of batched fits of the flagged genes
+        (gpc_opt_t.attempt0) and batched predictions.  The check is Monte-Carlo: parity with the reference is statistical."""
+        genes_index = np.asarray(list(genes_index), dtype=np.int64)
+        G = len(genes_index)
+        Xm = model.X.cpu().numpy()
+        x = (self.Z if self.sparse else Xm)
+        xtest = np.linspace(np.min(x), np.max(x), 100)[:, None] if Xm.shape[1] == 1 else Xm          # :969-972
+        Yk = Yfit[:, model.n_off:model.n_off + model.N]
+        a0 = np.zeros((G, 1), dtype=np.int32)
+        stats = np.zeros((G, 1, GPC_NSTAT))
+        theta = None
+        pending = np.arange(G)
+        diff = 0 if model.N < 100 else 1                                                         # :989-992
+        for _round in range(12):
+            if len(pending) == 0:
+                break
+            st = self._run([model], Yfit, hyp0, True, genes_index[pending], attempt0=_expand(a0, pending, len(Yfit), genes_index))
+            th = self._last_theta
+            if theta is None:
+                theta = torch.zeros(G, 1, model.P, dtype=torch.float64, device=th.device)
+            theta[torch.as_tensor(pending, device=th.device)] = th[:, :, :model.P]
+            stats[pending] = st
+            ok = (st[:, 0, S_STATUS] == 0)
+            c = st[:, 0, S_RESTARTS].astype(int)
+            chk = np.nonzero(ok & (c < 5))[0]
+            flag = np.zeros(len(pending), dtype=bool)
+            if len(chk):
+                mean = self._predictive_mean(model, th[torch.as_tensor(chk, device=th.device), 0, :model.P].contiguous(),
+                                             st[chk, 0], xtest, Yk[genes_index[pending[chk]]])
+                y = Yk[genes_index[pending[chk]]]
+                m_mean, m_max, m_min = mean.mean(axis=1), mean.max(axis=1), mean.min(axis=1)
+                y_mean, y_max, y_min = y.mean(axis=1), y.max(axis=1), y.min(axis=1)
+                bad = np.zeros(len(chk), dtype=bool)
+                if constant_of_one_sample:                                                       # :993-995
+                    bad |= (m_min < y_min) | (m_max > y_max) | (m_mean == 0.0)
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    dm = np.abs(np.round((m_mean - y_mean) / y_mean))
+                bad |= (y_mean > 0.0) & (((dm > diff) & ((m_min < y_min) | (m_max > y_max))) | (m_mean == 0.0))   # :997-1006
+                flag[chk] = bad
+            pos = ok & (st[:, 0, S_LL] > 0) & (c < 10) & (self.lik_name != "Gaussian")           # :518-525
+            redo = flag | pos
+            a0[pending[redo], 0] = np.minimum(c[redo] + 1 + pos[redo].astype(int), 10)
+            pending = pending[redo]
+        return stats, theta
+
+    def _run_safe(self, models, Yfit, hyp0, genes_index, models_number):
+        """The test with ``safe_mode=True``: model by model (the checks need each model's own fitted state)."""
+        genes_index = list(genes_index)
+        G, K = len(genes_index), len(models)
+        dist_saved, self.distributed = self.distributed, False          # the host-driven rounds run unsharded
+        try:
+            Pmax = max(m.P for m in models)
+            stats = np.zeros((G, K, GPC_NSTAT))
+            theta = None
+            gi = np.asarray(genes_index, dtype=np.int64)
+            for k, m in enumerate(models):
+                h = hyp0[:, k:k + 1].copy()
+                sub = np.arange(G)
+                if models_number == 2 and k == 1:
+                    alive = ~np.isnan(stats[:, 0, S_LL])                                   # :441-442
+                    stats[~alive, 1, S_LL], stats[~alive, 1, S_STATUS] = np.nan, 3
+                    sub = np.nonzero(alive)[0]
+                    if m.handoff_alpha:
+                        h[gi[sub], 0, 2] = stats[sub, 0, S_ALPHA]                          # :785-787 (first attempt only)
+                if len(sub) == 0:
+                    continue
+                st, th = self._safe_fit(m, Yfit, h, gi[sub], constant_of_one_sample=(models_number == 2 and k == 1))
+                stats[sub, k] = st[:, 0]
+                if theta is None:
+                    theta = torch.zeros(G, K, Pmax, dtype=torch.float64, device=th.device)
+                theta[torch.as_tensor(sub, device=th.device), k, :m.P] = th[:, 0]
+        finally:
+            self.distributed = dist_saved
+        self._last_theta, self._last_local_pos = theta, np.arange(G)
+        return stats
+
     # ------------------------------------------------------------------------------------------ run_test
     def run_test(self, lik_name, models_number, genes_index, branching=False):
         """Reference :393-428 with the gene loop replaced by one batched device fit."""
@@ -348,7 +541,7 @@ class Fit_GPcounts(object):
         if models_number == 1:
             models = [self._make_model("RBF", X)]
             hyp0 = self._hyp0(Y, X)[:, None, :]
-            stats = self._run(models, Yfit, hyp0, True, genes_index)
+            stats = self._run_safe(models, Yfit, hyp0, genes_index, 1) if self.safe_mode else self._run(models, Yfit, hyp0, True, genes_index)
             out = stats[:, :, S_LL]
             names = ["dynamic"]
         elif models_number == 2:
@@ -358,7 +551,7 @@ class Fit_GPcounts(object):
             # log-transformed y of the dynamic fit (:652 runs before :738 of the next model)
             yv2 = Yfit if (lik_name == "Gaussian" and self.transform) else None
             hyp0 = np.stack([self._hyp0(Y, X), self._hyp0(Y, X, kernel="CONST", y_for_var=yv2)], axis=1)
-            stats = self._run(models, Yfit, hyp0, True, genes_index)
+            stats = self._run_safe(models, Yfit, hyp0, genes_index, 2) if self.safe_mode else self._run(models, Yfit, hyp0, True, genes_index)
             ll = stats[:, :, S_LL].copy()
             bad = np.isnan(ll[:, 0]) | np.isnan(ll[:, 1])
             ll[bad, 1] = np.nan                                                         # :455-457
@@ -370,11 +563,15 @@ class Fit_GPcounts(object):
             models = [self._make_model("RBF", X), self._make_model("RBF", X1, n_off=0),
                       self._make_model("RBF", X2, n_off=h)]
             hyp0 = np.stack([self._hyp0(Y, X), self._hyp0(Y[:, :h], X1), self._hyp0(Y[:, h:], X2)], axis=1)
-            stats = self._run(models, Yfit, hyp0, False, genes_index)
+            stats = self._run_safe(models, Yfit, hyp0, genes_index, 3) if self.safe_mode else self._run(models, Yfit, hyp0, False, genes_index)
             ll = stats[:, :, S_LL]
             out = np.c_[ll, (ll[:, 1] + ll[:, 2]) - ll[:, 0]]                          # NaN propagates (:486-495)
             names = ["shared", "model_1", "model_2"]
         self._record_stats(stats, genes_index, names)
+        test_name = {1: "Infer_trajectory", 2: "One_sample_test", 3: "Two_samples_test"}[models_number]
+        Xs = [m.X.cpu().numpy() for m in models]
+        Ys = [Yfit[:, m.n_off:m.n_off + m.N] for m in models]
+        self._remember(test_name, models, names, stats, genes_index, Xs, Ys, [m.kernel for m in models])
         self.index = genes_index[-1] if genes_index else None
         if genes_index:
             self.y = Y[genes_index[-1]].reshape([-1, 1])
@@ -448,14 +645,34 @@ class Fit_GPcounts(object):
         self.model = FittedModel(stats[0, iMAP], theta, Xs[iMAP], self.y, kernel="BRANCH", xp=testTimes[iMAP],
                                  lik_name=lik_name)
         Xnew = np.linspace(min(self.X[:, 0]), max(self.X[:, 0]), 100).reshape(-1)[:, None]
+        # posterior predictive of the MAP model on both branches (reference :305-317)
+        x1 = np.c_[Xnew, np.ones(len(Xnew))[:, None]]
+        x2 = np.c_[Xnew, (np.ones(len(Xnew)) * 2)[:, None]]
+        Xtest = np.concatenate((x1, x2))
+        Xtest[np.where(Xtest[:, 0] <= self.model.kernel.xp), 1] = 1
+        mu = var = None
+        if theta is not None:
+            from . import predictive
+            th = torch.as_tensor(theta[None, :])
+            gauss = self.lik_name == "Gaussian"
+            mf, vf, cf = self._latent_at(models[iMAP], th, Xtest, Y=np.ascontiguousarray(Yfit[[g_last]]) if gauss else None,
+                                         full_cov=not gauss)
+            if gauss:
+                mu = mf.cpu().numpy()[0][:, None]
+                var = (vf.cpu().numpy()[0] + stats[0, iMAP, S_ALPHA])[:, None]            # predict_y: + noise variance
+            else:
+                dev = mf.device
+                m_, v_ = predictive.posterior_predictive(self.lik_name, mf, cf, torch.as_tensor(stats[0, iMAP, S_ALPHA:S_ALPHA + 1], device=dev),
+                                                         torch.as_tensor(stats[0, iMAP, S_KM:S_KM + 1], device=dev), branching=True,
+                                                         keep_samples=True)
+                mu, var = m_[0], v_[0]
         self.branching = False
         return {
             "geneName": self.genes_name,
             "branching_probability": ll,
             "branching_location": self.model.kernel.xp,
-            # posterior-predictive mean / variance need Monte-Carlo sampling (:305-317): outside the hot path
-            "mean": None,
-            "variance": None,
+            "mean": mu,
+            "variance": var,
             "Xnew": Xnew,
             "test_times": testTimes,
             "MAP_model": self.model,

@@ -32,11 +32,11 @@ class gpc_opt_t(C.Structure):
     _fields_ = [("m", C.c_int32), ("maxiter", C.c_int32), ("maxfun", C.c_int32), ("maxls", C.c_int32),
                 ("ftol", C.c_double), ("gtol", C.c_double),
                 ("variant", C.c_int32), ("trace_cap", C.c_int32), ("trace_gene", C.c_int32), ("trace_model", C.c_int32),
-                ("trace", C.c_void_p)]
+                ("trace", C.c_void_p), ("attempt0", C.c_void_p)]
 
 
 EXPORTS = ["gpc_default_opt", "gpc_param_count", "gpc_default_slots", "gpc_workspace_bytes", "gpc_elbo_grad",
-           "gpc_fit", "gpc_dbg_linalg", "gpc_dbg_linalg_scratch_bytes", "gpc_launch_count", "gpc_last_error_string", "gpc_version"]
+           "gpc_fit", "gpc_predict", "gpc_predict_workspace_bytes", "gpc_dbg_linalg", "gpc_dbg_linalg_scratch_bytes", "gpc_launch_count", "gpc_last_error_string", "gpc_version"]
 
 _lib = None
 
@@ -68,6 +68,11 @@ def load():
                             C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t,
                             C.c_int32, C.c_void_p]
     lib.gpc_fit.restype = C.c_int
+    lib.gpc_predict_workspace_bytes.argtypes = [P(gpc_model_t), C.c_int32, C.c_int32]
+    lib.gpc_predict_workspace_bytes.restype = C.c_size_t
+    lib.gpc_predict.argtypes = [P(gpc_model_t), C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p]
+    lib.gpc_predict.restype = C.c_int
     lib.gpc_dbg_linalg.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_size_t, C.c_void_p]
     lib.gpc_dbg_linalg.restype = C.c_int

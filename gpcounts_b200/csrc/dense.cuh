@@ -33,7 +33,7 @@
 
 enum { F_A_LOWER = 1, F_A_UPPER = 2, F_B_LOWER = 4, F_B_UPPER = 8, F_C_LOWER = 16 };
 
-extern __shared__ __align__(16) unsigned char g_smem[];
+extern __shared__ __align__(128) unsigned char g_smem[];   // 128 B: TMA destinations live in it
 
 __device__ __forceinline__ struct CtaSmem* cta_arena();
 

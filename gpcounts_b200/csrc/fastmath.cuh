@@ -32,6 +32,14 @@ GPC_HD long long gpc_double_to_bits(double d) {
 #endif
 }
 
+GPC_HD int gpc_lo_int(double d) {
+#ifdef __CUDA_ARCH__
+    return __double2loint(d);
+#else
+    return (int)(unsigned)(gpc_double_to_bits(d) & 0xffffffffLL);
+#endif
+}
+
 // 1 / x for finite x != 0 (x = +-inf -> +-0, NaN -> NaN): hardware seed (MUFU.RCP64H, ~20 bits) + Newton steps.
 GPC_HD double gpc_rcp(double x) {
 #ifdef __CUDA_ARCH__
@@ -55,6 +63,7 @@ template <int K>
 GPC_HD void gpc_exp_v(const double (&x)[K], double (&out)[K]) {
     const double LOG2E = 1.4426950408889634, LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
     double r[K], p[K], fn[K];
+    int ni[K];
 #ifdef __CUDACC__
 #pragma unroll
 #endif
@@ -62,7 +71,11 @@ GPC_HD void gpc_exp_v(const double (&x)[K], double (&out)[K]) {
         double xc = x[k];
         if (xc < -1000.0) xc = -1000.0;          // selects: NaN compares false and passes through
         if (xc > 1000.0) xc = 1000.0;
-        fn[k] = rint(xc * LOG2E);
+        // round-to-nearest through the 2^52 + 2^51 shift (two adds instead of FRND + F2I, which issue at a quarter rate);
+        // the integer n sits in the low word of the shifted value (|n| <= 1443)
+        const double sh = fma(xc, LOG2E, 6755399441055744.0);
+        ni[k] = gpc_lo_int(sh);
+        fn[k] = sh - 6755399441055744.0;
         r[k] = fma(fn[k], -LN2_HI, xc);
         r[k] = fma(fn[k], -LN2_LO, r[k]);
         p[k] = 1.6059043836821613e-10;           // 1/13!
@@ -84,7 +97,7 @@ GPC_HD void gpc_exp_v(const double (&x)[K], double (&out)[K]) {
 #endif
     for (int k = 0; k < K; ++k) {
         p[k] = fma(p[k], r[k], 1.0);
-        const int n = (int)fn[k];                // NaN -> 0 on the device; the product below stays NaN through p
+        const int n = ni[k];                     // garbage for NaN input; the product below stays NaN through p
         const int n1 = n >> 1, n2 = n - n1;
         const double s1 = gpc_bits_to_double((long long)(n1 + 1023) << 52);
         const double s2 = gpc_bits_to_double((long long)(n2 + 1023) << 52);
@@ -206,3 +219,18 @@ GPC_HD void gpc_lgamma_digamma_v(const double (&x)[K], double (&lg)[K], double (
         dg[k] = dgX - Q[k] * gpc_rcp(P[k]);
     }
 }
+
+#ifdef __CUDACC__
+// x^-1/2 without a slow-path branch: hardware seed (MUFU.RSQ64H) + two third-order Newton steps.
+__device__ __forceinline__ double gpc_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {                       // third-order steps: 20 -> 60 -> 180 bits
+        const double e = fma(-x * y, y, 1.0);
+        y = fma(y * e, fma(0.375, e, 0.5), y);
+    }
+    return y;
+}
+
+#endif

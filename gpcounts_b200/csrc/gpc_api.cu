@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include "../../include/gpcounts_b200.h"
 #define GPC_VARIANT t256
@@ -60,25 +62,68 @@ static const double H_GH_W[GPC_NGH] = {
     7.8025564785320632e-06, 1.0860693707692815e-07, 4.3993409922731809e-10, 2.2293936455341505e-13};
 
 static size_t smem_bytes() { return eval_smem_bytes() + sizeof(OptSmem); }
+#define GPC_API_SMALL_NMAX 48     // = GPC_SMALL_NMAX of vgp_small.cuh (compiled into gpc_small.cu only)
+
+// TMA descriptor of a gene-major FP64 matrix [D][ld]: box = 64 columns x 1 row, i.e. one column tile of one gene's counts
+// (or scale factors); columns past `ld` read as zeros.  Needs a 16-byte aligned base and row pitch (ld even); returns false
+// otherwise (the kernels then read the rows with ordinary loads).  cuTensorMapEncodeTiled is resolved through the runtime
+// (no link-time dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool make_row_tile_map(CUtensorMap* tm, const double* base, int64_t D, int64_t ld) {
+    static EncodeTiledFn fn = nullptr;
+    static std::mutex mu;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!fn) {
+            void* p = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
+            fn = (EncodeTiledFn)p;
+        }
+    }
+    if (((uintptr_t)base & 15) || (ld & 1) || D < 1 || ld < 1) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)D};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(double)};
+    const cuuint32_t box[2] = {64, 1}, estr[2] = {1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 // Kernel instantiations (kernels.cuh): [0] every evaluator; [1] dense evaluators only, two CTAs per SM;
-// [2] fused SVGP evaluator only.
-static VariantOps g_ops[3];
+// [2] fused SVGP evaluator only; [3] on-chip small-N VGP evaluator, 64-thread CTAs, 8-9 per SM.
+#define GPC_NVARIANTS 4
+static VariantOps g_ops[GPC_NVARIANTS];
 VariantOps gpc_variant_ops_d128();     // gpc_dense.cu
 VariantOps gpc_variant_ops_f256();     // gpc_fused.cu
+VariantOps gpc_variant_ops_s64();      // gpc_small.cu
 
 static bool host_use_fused(const gpc_model_t& md) {
     return md.kind == GPC_SVGP && md.M <= 64 && md.d <= 2 && md.kernel != GPC_BRANCH;
 }
 
+static bool host_use_small(const gpc_model_t& md) {
+    return md.kind == GPC_VGP && md.N <= GPC_API_SMALL_NMAX;
+}
+
+static int models_nmax(const gpc_model_t* models, int n_models) {
+    int n = 1;
+    for (int k = 0; k < n_models; ++k) n = std::max(n, (int)models[k].N);
+    return n;
+}
+
 static int pick_variant(const gpc_model_t* models, int n_models, int forced = -1) {
-    bool any_fused = false, all_fused = true;
+    bool any_fused = false, all_fused = true, all_small = true;
     for (int k = 0; k < n_models; ++k) {
         const bool f = host_use_fused(models[k]);
         any_fused = any_fused || f;
         all_fused = all_fused && f;
+        all_small = all_small && host_use_small(models[k]);
     }
     if (forced == 0) return 0;       // instantiation [0] holds every evaluator (A/B measurements through gpc_opt_t.variant)
+    if (forced == 1 && !any_fused) return 1;
+    if (all_small) return 3;
     return all_fused ? 2 : (any_fused ? 0 : 1);
 }
 
@@ -95,7 +140,8 @@ static int ensure_init() {
     g_ops[0] = gpc_variant_ops_t256();
     g_ops[1] = gpc_variant_ops_d128();
     g_ops[2] = gpc_variant_ops_f256();
-    for (int v = 0; v < 3; ++v)
+    g_ops[3] = gpc_variant_ops_s64();
+    for (int v = 0; v < GPC_NVARIANTS; ++v)
         if (g_ops[v].upload_constants(z, w) != 0)
             return set_err(GPC_E_LAUNCH, "constant upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     cudaFuncSetAttribute(k_dbg_linalg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes());
@@ -124,6 +170,7 @@ void gpc_default_opt(gpc_opt_t* opt) {
     opt->m = 10; opt->maxiter = 5000; opt->maxfun = 15000; opt->maxls = 20;
     opt->ftol = 2.220446049250313e-09; opt->gtol = 1e-5;
     opt->variant = -1; opt->trace_cap = 0; opt->trace_gene = -1; opt->trace_model = -1; opt->trace = nullptr;
+    opt->attempt0 = nullptr;
 }
 
 int64_t gpc_param_count(const gpc_model_t* model) {
@@ -134,14 +181,15 @@ int64_t gpc_param_count(const gpc_model_t* model) {
 int32_t gpc_default_slots(const gpc_model_t* models, int32_t n_models) {
     int dev = 0, sms = 148, per_sm = 1;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (ensure_init() == 0) per_sm = g_ops[models ? pick_variant(models, n_models) : 0].occupancy();
+    const int v = models ? pick_variant(models, n_models) : 0;
+    if (ensure_init() == 0) per_sm = g_ops[v].occupancy(models ? models_nmax(models, n_models) : 1);
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 2) per_sm = 2;
+    if (per_sm > (v == 3 ? 12 : 2)) per_sm = (v == 3 ? 12 : 2);
     return sms * per_sm;
 }
 
 size_t gpc_workspace_bytes(const gpc_model_t* models, int32_t n_models, const gpc_opt_t* opt, int32_t n_slots) {
-    const WsLayout L = make_layout(models, n_models, opt ? opt->m : 0);
+    const WsLayout L = make_layout(models, n_models, opt ? opt->m : 0, pick_variant(models, n_models, opt ? opt->variant : -1) == 3);
     return 256 + pad8(sizeof(ModelDev) * (size_t)n_models) + (size_t)n_slots * L.slot * sizeof(double);
 }
 
@@ -154,7 +202,7 @@ int gpc_elbo_grad(const gpc_model_t* model, int32_t D, const double* Y, const do
         return set_err(GPC_E_ARG, "gpc_elbo_grad: null or invalid argument%s");
     if ((rc = check_model(*model))) return rc;
     if (zset < 0 || (model->Z && zset >= model->n_zsets)) return set_err(GPC_E_ARG, "gpc_elbo_grad: zset out of range%s");
-    const WsLayout L = make_layout(model, 1, 0);
+    const WsLayout L = make_layout(model, 1, 0, pick_variant(model, 1) == 3);
     if (workspace_bytes < 256 + (size_t)n_slots * L.slot * sizeof(double))
         return set_err(GPC_E_WORKSPACE, "gpc_elbo_grad: workspace too small%s");
     if (D == 0) return 0;
@@ -166,9 +214,10 @@ int gpc_elbo_grad(const gpc_model_t* model, int32_t D, const double* Y, const do
     a.queue = (int*)workspace;
     a.ws = (double*)((char*)workspace + 256);
     a.lay = L;
+    a.use_tma = make_row_tile_map(&a.tmY, Y, D, ldy) && (!scale || make_row_tile_map(&a.tmS, scale, D, ldy));
     cudaMemsetAsync(a.queue, 0, 256, s);
     const int grid = n_slots < D ? n_slots : D;
-    cudaError_t e = g_ops[pick_variant(model, 1)].launch_eval(&a, grid, s);
+    cudaError_t e = g_ops[pick_variant(model, 1)].launch_eval(&a, grid, model->N, s);
     ++g_launches;
     if (e != cudaSuccess) return set_err(GPC_E_LAUNCH, "gpc_elbo_grad launch: %s", cudaGetErrorString(e));
     return 0;
@@ -190,7 +239,8 @@ int gpc_fit(const gpc_model_t* models, int32_t n_models, int32_t chain, const gp
         pmax = std::max(pmax, gpc_param_count(&models[k]));
     }
     if (out_theta && ld_theta < pmax) return set_err(GPC_E_ARG, "gpc_fit: ld_theta smaller than the parameter count%s");
-    const WsLayout L = make_layout(models, n_models, opt->m);
+    const int variant = pick_variant(models, n_models, opt->variant);
+    const WsLayout L = make_layout(models, n_models, opt->m, variant == 3);
     const size_t hdr = 256 + pad8(sizeof(ModelDev) * (size_t)n_models);
     if (workspace_bytes < hdr + (size_t)n_slots * L.slot * sizeof(double))
         return set_err(GPC_E_WORKSPACE, "gpc_fit: workspace too small%s");
@@ -208,11 +258,13 @@ int gpc_fit(const gpc_model_t* models, int32_t n_models, int32_t chain, const gp
     a.queue = (int*)workspace;
     a.ws = (double*)((char*)workspace + hdr);
     a.lay = L;
+    a.nmax = models_nmax(models, n_models);
     a.trace = opt->trace; a.trace_cap = opt->trace_cap; a.trace_gene = opt->trace_gene; a.trace_model = opt->trace_model;
+    a.use_tma = make_row_tile_map(&a.tmY, Y, D, ldy) && (!scale || make_row_tile_map(&a.tmS, scale, D, ldy));
     cudaMemsetAsync(a.queue, 0, 256, s);
     const int n_jobs = chain ? D : D * n_models;
     const int grid = n_slots < n_jobs ? n_slots : n_jobs;
-    cudaError_t e = g_ops[pick_variant(models, n_models, opt->variant)].launch_fit(&a, grid, s);
+    cudaError_t e = g_ops[variant].launch_fit(&a, grid, models_nmax(models, n_models), s);
     ++g_launches;
     if (e != cudaSuccess) return set_err(GPC_E_LAUNCH, "gpc_fit launch: %s", cudaGetErrorString(e));
     return 0;
@@ -221,6 +273,53 @@ int gpc_fit(const gpc_model_t* models, int32_t n_models, int32_t chain, const gp
 size_t gpc_dbg_linalg_scratch_bytes(int32_t batch, int32_t n) {
     const size_t nblk = (size_t)(n + GPC_BLK - 1) / GPC_BLK;
     return ((size_t)nblk * GPC_BLK * GPC_BLK + (size_t)n * n) * (size_t)batch * sizeof(double);
+}
+
+static void predict_layout(const gpc_model_t& md, int T, PredictArgs& a) {
+    const bool sparse = md.kind == GPC_SVGP || md.kind == GPC_SGPR;
+    const size_t mr = sparse ? md.M : md.N;
+    a.sq = pad8(mr * mr);
+    a.dinv = (size_t)((mr + GPC_BLK - 1) / GPC_BLK) * GPC_BLK * GPC_BLK;
+    a.rect = pad8(mr * (size_t)T);
+    a.vec = pad8(mr);
+    a.slot = 3 * a.sq + a.dinv + 2 * a.rect + a.vec;
+}
+
+size_t gpc_predict_workspace_bytes(const gpc_model_t* model, int32_t T, int32_t n_slots) {
+    PredictArgs a;
+    predict_layout(*model, T, a);
+    return 256 + (size_t)n_slots * a.slot * sizeof(double);
+}
+
+int gpc_predict(const gpc_model_t* model, int32_t D, const double* Y, int64_t ldy, const double* theta, int64_t ld_theta,
+                int32_t zset, const double* Xnew, int32_t T, double* out_mean, double* out_var, double* out_cov,
+                void* workspace, size_t workspace_bytes, int32_t n_slots, void* stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!model || D < 0 || !theta || !Xnew || T < 1 || !out_mean || !out_var || !workspace || n_slots < 1)
+        return set_err(GPC_E_ARG, "gpc_predict: null or invalid argument%s");
+    if ((rc = check_model(*model))) return rc;
+    if (model->kind == GPC_SGPR) return set_err(GPC_E_UNSUPPORTED, "gpc_predict: SGPR prediction is not provided%s");
+    if (model->kind == GPC_GPR && !Y) return set_err(GPC_E_ARG, "gpc_predict: GPR prediction needs the data Y%s");
+    if (ld_theta < gpc_param_count(model)) return set_err(GPC_E_ARG, "gpc_predict: ld_theta smaller than the parameter count%s");
+    if (zset < 0 || (model->Z && zset >= model->n_zsets)) return set_err(GPC_E_ARG, "gpc_predict: zset out of range%s");
+    PredictArgs a;
+    predict_layout(*model, T, a);
+    if (workspace_bytes < 256 + (size_t)n_slots * a.slot * sizeof(double))
+        return set_err(GPC_E_WORKSPACE, "gpc_predict: workspace too small%s");
+    if (D == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    a.md = to_dev(*model);
+    a.D = D; a.T = T; a.zset = zset; a.Y = Y; a.theta = theta; a.Xnew = Xnew; a.ldy = ldy; a.ld_theta = ld_theta;
+    a.mean = out_mean; a.var = out_var; a.cov = out_cov;
+    a.queue = (int*)workspace;
+    a.ws = (double*)((char*)workspace + 256);
+    cudaMemsetAsync(a.queue, 0, 256, s);
+    const int grid = n_slots < D ? n_slots : D;
+    cudaError_t e = g_ops[1].launch_predict(&a, grid, s);
+    ++g_launches;
+    if (e != cudaSuccess) return set_err(GPC_E_LAUNCH, "gpc_predict launch: %s", cudaGetErrorString(e));
+    return 0;
 }
 
 int gpc_dbg_linalg(int32_t op, int32_t batch, int32_t n, int32_t nrhs, double* A, double* B, int32_t* status,
@@ -243,7 +342,7 @@ int64_t gpc_launch_count(void) { return g_launches.load(); }
 #ifdef GPC_PHASE_PROF
 // profiling build only (tools/phase_prof.py): read and reset the phase timers of the fused evaluator of one instantiation
 int gpc_dbg_phase_prof(int variant, unsigned long long* out16) {
-    if (ensure_init() != 0 || variant < 0 || variant > 2 || !g_ops[variant].read_prof) return -1;
+    if (ensure_init() != 0 || variant < 0 || variant >= GPC_NVARIANTS || !g_ops[variant].read_prof) return -1;
     return g_ops[variant].read_prof(out16);
 }
 #endif

@@ -14,6 +14,7 @@
 #pragma once
 #include <algorithm>
 #include <math.h>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include "../../include/gpcounts_b200.h"
 
@@ -21,11 +22,12 @@
 // own, anonymous-namespace copy of the device code and of the argument types)
 struct VariantOps {
     int (*upload_constants)(const double* z, const double* w);
-    size_t (*smem_bytes)();
-    int (*occupancy)();
-    cudaError_t (*launch_fit)(const void* fit_args, int grid, cudaStream_t s);
-    cudaError_t (*launch_eval)(const void* eval_args, int grid, cudaStream_t s);
+    size_t (*smem_bytes)(int nmax);             // nmax: largest N of the models (sizes the arena of the small instantiation)
+    int (*occupancy)(int nmax);
+    cudaError_t (*launch_fit)(const void* fit_args, int grid, int nmax, cudaStream_t s);
+    cudaError_t (*launch_eval)(const void* eval_args, int grid, int nmax, cudaStream_t s);
     int (*read_prof)(unsigned long long* out16);   // profiling build only (GPC_PHASE_PROF), else nullptr
+    cudaError_t (*launch_predict)(const void* predict_args, int grid, cudaStream_t s);   // dense instantiations only, else nullptr
 };
 
 namespace {   // everything below is private to the including translation unit
@@ -52,7 +54,7 @@ static int model_mv(const gpc_model_t& md) {
     return md.kind == GPC_VGP ? md.N : (md.kind == GPC_SVGP ? md.M : 0);
 }
 
-static WsLayout make_layout(const gpc_model_t* models, int n_models, int m) {
+static WsLayout make_layout(const gpc_model_t* models, int n_models, int m, bool small_only = false) {
     WsLayout L{};
     L.m = m;
     for (int k = 0; k < n_models; ++k) {
@@ -67,6 +69,7 @@ static WsLayout make_layout(const gpc_model_t* models, int n_models, int m) {
         L.vec = std::max(L.vec, pad8((size_t)std::max(md.N, md.M)));
         L.pvec = std::max(L.pvec, pad8(P));
     }
+    if (small_only) { L.sq = 0; L.dinv = 0; L.rect = 0; L.vec = 0; }   // the on-chip small-N evaluator keeps its factors in shared memory
     L.slot = 7 * L.sq + 2 * L.dinv + 4 * L.rect + 4 * L.vec + (size_t)(6 + 2 * m) * L.pvec;
     return L;
 }
@@ -83,6 +86,7 @@ __device__ __forceinline__ SlotWs carve(double* base, const WsLayout& L) {
     w.x = p; p += L.pvec; w.g = p; p += L.pvec; w.d = p; p += L.pvec;
     w.xold = p; p += L.pvec; w.gold = p; p += L.pvec; w.z = p; p += L.pvec;
     w.WS = p; p += (size_t)L.m * L.pvec; w.WY = p;
+    w.tmY = nullptr; w.tmS = nullptr; w.row = 0; w.fresh = 1; w.arena_off = GPC_SMALL_ARENA_OFF;
     return w;
 }
 
@@ -98,6 +102,11 @@ __host__ __device__ static inline ModelDev to_dev(const gpc_model_t& md) {
 
 // ---------------------------------------------------------------------------------------------- kernels
 #define GPC_MAX_MODELS_CONST 64
+#ifdef GPC_SMALL_ONLY
+#define GPC_SMALL_NMAX_OR_0 GPC_SMALL_NMAX
+#else
+#define GPC_SMALL_NMAX_OR_0 0
+#endif
 struct FitArgs {
     const ModelDev* models;   // device array
     int n_models, chain, D;
@@ -110,6 +119,10 @@ struct FitArgs {
     WsLayout lay;
     double* trace;            // debug: evaluation trace of (trace_gene, trace_model), 8 doubles per evaluation
     int trace_cap, trace_gene, trace_model;
+    int nmax;                 // largest N of the models (sizes the shared-memory carve of the small instantiation)
+    int use_tma;              // tmY (and tmS when scale != nullptr) are valid
+    alignas(64) CUtensorMap tmY;   // Y     as a 2-D FP64 tensor [D][ldy], box 64 x 1 (one column tile of one gene)
+    alignas(64) CUtensorMap tmS;   // scale likewise
 };
 
 
@@ -119,12 +132,19 @@ struct FitArgs {
 #endif
 
 __host__ __device__ constexpr size_t eval_smem_bytes() {
-#ifdef GPC_DENSE_ONLY
+#if defined(GPC_SMALL_ONLY)
+    return GPC_SMALL_ARENA_OFF;      // [OptSmem | evaluator arena sized by N at launch]; see small_total_smem()
+#elif defined(GPC_DENSE_ONLY)
     return (sizeof(CtaSmem) + 15) & ~(size_t)15;
 #else
-    return ((sizeof(CtaSmem) > sizeof(FusedSmem) ? sizeof(CtaSmem) : sizeof(FusedSmem)) + 15) & ~(size_t)15;
+    return ((sizeof(CtaSmem) > sizeof(FusedSmem) ? sizeof(CtaSmem) : sizeof(FusedSmem)) + 127) & ~(size_t)127;
 #endif
 }
+#if defined(GPC_SMALL_ONLY)
+static_assert(sizeof(OptSmem) <= GPC_SMALL_ARENA_OFF, "OptSmem must fit in front of the small evaluator's arena");
+#else
+static_assert(eval_smem_bytes() + sizeof(OptSmem) + 1024 <= 232448, "shared memory of the fit kernel exceeds 227 KB");
+#endif
 
 __device__ __forceinline__ double softplus_inv_d(double p) { return p + log(-expm1(-p)); }
 
@@ -148,7 +168,8 @@ __device__ bool fit_one(const FitArgs& a, int g, int k, double prev_alpha, const
     long long eval_cycles = 0;
     const long long t_start = clock64();
     OptResult r;
-    int attempt = 0;
+    int attempt = a.opt.attempt0 ? a.opt.attempt0[(size_t)g * a.n_models + k] : 0;      // host-driven restarts (safe_mode)
+    if (attempt > max_restart) attempt = max_restart;
     bool ok = false;
     for (;; ++attempt) {
         double var, ls, alpha, km;
@@ -189,6 +210,8 @@ __device__ bool fit_one(const FitArgs& a, int g, int k, double prev_alpha, const
         __syncthreads();
         const double* Z = md.Z ? md.Z + (size_t)(md.n_zsets > 1 ? attempt : 0) * md.M * md.d : nullptr;
         if (attempt == 0 && md.Zgene) Z = md.Zgene + (size_t)g * md.M * md.d;
+        if (tid == 0) const_cast<SlotWs&>(ws).fresh = 1;      // the slot workspace lives in shared memory (s_ws)
+        __syncthreads();
         OptTrace tr{nullptr, 0, 0};
         if (a.trace && g == a.trace_gene && k == a.trace_model && attempt == 0) { tr.buf = a.trace; tr.cap = a.trace_cap; }
         r = lbfgsb_minimize(md, Z, y, scale, a.opt, ws, sm, os, &tr);
@@ -222,12 +245,30 @@ __device__ bool fit_one(const FitArgs& a, int g, int k, double prev_alpha, const
     return ok;
 }
 
-__global__ void __launch_bounds__(GPC_THREADS, GPC_MIN_BLOCKS) GPC_KNAME(k_fit)(FitArgs a) {
+__global__ void __launch_bounds__(GPC_THREADS, GPC_MIN_BLOCKS) GPC_KNAME(k_fit)(const __grid_constant__ FitArgs a) {
     CtaSmem* sm = reinterpret_cast<CtaSmem*>(g_smem);
+#if defined(GPC_SMALL_ONLY)
+    OptSmem* os = reinterpret_cast<OptSmem*>(g_smem);           // the evaluator's arena follows at GPC_SMALL_ARENA_OFF
+#else
     OptSmem* os = reinterpret_cast<OptSmem*>(g_smem + eval_smem_bytes());
+#endif
     __shared__ int s_job;
     __shared__ SlotWs s_ws;
-    if (threadIdx.x == 0) s_ws = carve(a.ws + (size_t)blockIdx.x * a.lay.slot, a.lay);
+    if (threadIdx.x == 0) {
+        s_ws = carve(a.ws + (size_t)blockIdx.x * a.lay.slot, a.lay);
+        if (a.use_tma) { s_ws.tmY = &a.tmY; s_ws.tmS = a.scale ? &a.tmS : nullptr; }
+#if defined(GPC_SMALL_ONLY)
+        {
+            // the six optimiser vectors (P <= 1228 doubles each) sit in shared memory in front of the evaluator's arena:
+            // at N = 18 an L-BFGS iteration is a chain of ~20 dependent vector accesses, each an L2 round trip otherwise
+            const int n = a.nmax < 1 ? 1 : (a.nmax > GPC_SMALL_NMAX ? GPC_SMALL_NMAX : a.nmax);
+            double* v = reinterpret_cast<double*>(g_smem + GPC_SMALL_ARENA_OFF);
+            const size_t pv = GPC_SMALL_PVEC(n);
+            s_ws.x = v; s_ws.g = v + pv; s_ws.d = v + 2 * pv; s_ws.xold = v + 3 * pv; s_ws.gold = v + 4 * pv; s_ws.z = v + 5 * pv;
+            s_ws.arena_off = GPC_SMALL_ARENA_OFF + (int)GPC_SMALL_VEC_BYTES(n);
+        }
+#endif
+    }
     __syncthreads();
     const SlotWs& ws = s_ws;
     const int n_jobs = a.chain ? a.D : a.D * a.n_models;
@@ -237,6 +278,8 @@ __global__ void __launch_bounds__(GPC_THREADS, GPC_MIN_BLOCKS) GPC_KNAME(k_fit)(
         __syncthreads();
         const int job = s_job;
         if (job >= n_jobs) break;
+        if (threadIdx.x == 0) s_ws.row = a.chain ? job : job / a.n_models;
+        __syncthreads();
         if (a.chain) {
             double prev_alpha = -1.0;
             bool alive = true;
@@ -271,16 +314,28 @@ struct EvalArgs {
     double* ws;
     int* queue;
     WsLayout lay;
+    int use_tma;
+    alignas(64) CUtensorMap tmY;
+    alignas(64) CUtensorMap tmS;
 };
 
-__global__ void __launch_bounds__(GPC_THREADS, GPC_MIN_BLOCKS) GPC_KNAME(k_elbo_grad)(EvalArgs a) {
+__global__ void __launch_bounds__(GPC_THREADS, GPC_MIN_BLOCKS) GPC_KNAME(k_elbo_grad)(const __grid_constant__ EvalArgs a) {
     CtaSmem* sm = reinterpret_cast<CtaSmem*>(g_smem);
     __shared__ int s_job;
-    const SlotWs ws = carve(a.ws + (size_t)blockIdx.x * a.lay.slot, a.lay);
-    const ModelDev md = a.md;
+    __shared__ SlotWs s_ws;
+    if (threadIdx.x == 0) {
+        s_ws = carve(a.ws + (size_t)blockIdx.x * a.lay.slot, a.lay);
+        if (a.use_tma) { s_ws.tmY = &a.tmY; s_ws.tmS = a.scale ? &a.tmS : nullptr; }
+    }
+    const SlotWs& ws = s_ws;
+    // the descriptor is passed by reference into out-of-line evaluators: a per-thread copy would live in local memory
+    // (L2 round trips behind the small L1 that the shared-memory carve-out leaves), so it sits in shared memory as in k_fit
+    __shared__ ModelDev s_md;
+    if (threadIdx.x == 0) s_md = a.md;
+    const ModelDev& md = s_md;
     while (true) {
         __syncthreads();
-        if (threadIdx.x == 0) s_job = atomicAdd(a.queue, 1);
+        if (threadIdx.x == 0) { s_job = atomicAdd(a.queue, 1); s_ws.row = s_job; s_ws.fresh = 1; }
         __syncthreads();
         const int g = s_job;
         if (g >= a.D) break;
@@ -300,34 +355,153 @@ __global__ void __launch_bounds__(GPC_THREADS, GPC_MIN_BLOCKS) GPC_KNAME(k_elbo_
     }
 }
 
-static size_t GPC_KNAME(v_smem_bytes)() { return eval_smem_bytes() + sizeof(OptSmem); }
+// ---------------------------------------------------------------------------------------------- posterior prediction
+// Replaces `model.predict_f(Xnew)` / `predict_y` / the mean and covariance behind `predict_f_samples` of a fitted gpflow model
+// (reference: load_predict_models GPcounts_Module.py:930-945, infer_branching :305-317, test_local_optima_case1 :962-980),
+// batched over genes from the fitted parameter vectors theta-hat that gpc_fit returns:
+//   VGP / SVGP (whitened):  A = Lm^-1 K(Zr, Xnew), Zr = X | Z;  mean = A^T q_mu;  cov = K(Xnew, Xnew) - A^T A + (Lq^T A)^T (Lq^T A)
+//   GPR:                    A = L^-1 K(X, Xnew), L = chol(K + s2 I), v = L^-1 y;  mean = A^T v;  cov = K(Xnew, Xnew) - A^T A
+// `var` is the diagonal of cov (latent f; predict_y adds the Gaussian noise on the host); `cov` (T x T) is optional.
+struct PredictArgs {
+    ModelDev md;
+    int D, T, zset;
+    const double *Y, *theta, *Xnew;
+    long long ldy, ld_theta;
+    double *mean, *var, *cov;
+    double* ws;
+    int* queue;
+    size_t sq, dinv, rect, vec, slot;     // doubles
+};
+
+#if !defined(GPC_FUSED_ONLY) && !defined(GPC_SMALL_ONLY)
+__global__ void __launch_bounds__(GPC_THREADS, GPC_MIN_BLOCKS) GPC_KNAME(k_predict)(const __grid_constant__ PredictArgs a) {
+    CtaSmem* sm = reinterpret_cast<CtaSmem*>(g_smem);
+    __shared__ int s_job;
+    __shared__ ModelDev s_md;
+    if (threadIdx.x == 0) s_md = a.md;
+    const ModelDev& md = s_md;
+    const int tid = threadIdx.x, T = a.T;
+    double* base = a.ws + (size_t)blockIdx.x * a.slot;
+    double* K0 = base; double* L = K0 + a.sq; double* Lq = L + a.sq; double* dinv = Lq + a.sq;
+    double* A = dinv + a.dinv; double* B = A + a.rect; double* v = B + a.rect;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_job = atomicAdd(a.queue, 1);
+        __syncthreads();
+        const int g = s_job;
+        if (g >= a.D) break;
+        const double* theta = a.theta + (size_t)g * a.ld_theta;
+        const bool sparse = md.kind == GPC_SVGP || md.kind == GPC_SGPR;
+        const int Mr = sparse ? md.M : md.N;                       // rows of the factor
+        const double* Zr = sparse ? md.Z + (size_t)a.zset * md.M * md.d : md.X;
+        const Hyper h = hyper_from_theta(md, theta);
+        KernParams kp;
+        kern_setup(kp, md, h.var, h.ls);
+        const double noise = (md.kernel == GPC_BRANCH ? GPC_BRANCH_NOISE : 0.0);
+        const double shift = (md.kind == GPC_GPR ? h.alpha : md.jitter) + noise;
+        const double kdiag = h.var + noise;
+        double* mean = a.mean + (size_t)g * T;
+        double* var = a.var + (size_t)g * T;
+        double* cov = a.cov ? a.cov + (size_t)g * T * T : nullptr;
+        bool ok = md.kind != GPC_SGPR;                               // SGPR prediction is not provided (fit only)
+        if (ok) {
+            build_gram_square(kp, Mr, Zr, shift, K0, L);
+            ok = cta_potrf(Mr, L, Mr, dinv, sm);
+        }
+        if (!ok) {
+            for (int t = tid; t < T; t += GPC_THREADS) { mean[t] = NAN; var[t] = NAN; }
+            if (cov) for (int t = tid; t < T * T; t += GPC_THREADS) cov[t] = NAN;
+            continue;
+        }
+        GPC_FOR_2D(Mr, T, i, t) {
+            bool cross;
+            const double r2 = kern_r2(kp, Zr + (size_t)i * kp.d, a.Xnew + (size_t)t * kp.d, cross);
+            A[idx] = kern_val(kp, r2, cross);
+        }
+        __syncthreads();
+        cta_trsm_left(Mr, T, L, Mr, dinv, A, T, sm);               // A = L^-1 K(Zr, Xnew)
+        const double* wvec;                                          // mean = A^T wvec
+        if (md.kind == GPC_GPR) {
+            const double* y = a.Y + (size_t)g * a.ldy + md.n_off;
+            for (int n = tid; n < Mr; n += GPC_THREADS) v[n] = y[n];
+            __syncthreads();
+            cta_trsm_left(Mr, 1, L, Mr, dinv, v, 1, sm);
+            wvec = v;
+        } else {
+            wvec = theta + GPC_NHYP;                                 // q_mu
+            unpack_lq(Mr, theta + GPC_NHYP + Mr, Lq);
+            cta_gemm<true, false>(Mr, T, Mr, 1.0, Lq, Mr, A, T, 0.0, B, T, F_A_UPPER, sm);   // B = Lq^T A
+        }
+        for (int t = tid; t < T; t += GPC_THREADS) {
+            double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            for (int i = 0; i < Mr; ++i) {
+                const double av = A[(size_t)i * T + t];
+                s1 = fma(av, wvec[i], s1);
+                s2 = fma(av, av, s2);
+                if (md.kind != GPC_GPR) { const double bv = B[(size_t)i * T + t]; s3 = fma(bv, bv, s3); }
+            }
+            mean[t] = s1;
+            var[t] = (kdiag - s2) + s3;
+        }
+        if (cov) {
+            // cov = K(Xnew, Xnew) - A^T A (+ B^T B); the BranchKernel adds its noise only on the diagonal of a square Gram
+            GPC_FOR_2D(T, T, i, t) {
+                bool cross;
+                const double r2 = kern_r2(kp, a.Xnew + (size_t)i * kp.d, a.Xnew + (size_t)t * kp.d, cross);
+                cov[idx] = kern_val(kp, r2, cross) + (i == t ? noise : 0.0);
+            }
+            __syncthreads();
+            cta_gemm<true, false>(T, T, Mr, -1.0, A, T, A, T, 1.0, cov, T, 0, sm);
+            if (md.kind != GPC_GPR) cta_gemm<true, false>(T, T, Mr, 1.0, B, T, B, T, 1.0, cov, T, 0, sm);
+        }
+    }
+}
+
+static cudaError_t GPC_KNAME(v_launch_predict)(const void* a, int grid, cudaStream_t s) {
+    GPC_KNAME(k_predict)<<<grid, GPC_THREADS, eval_smem_bytes() + sizeof(OptSmem), s>>>(*static_cast<const PredictArgs*>(a));
+    return cudaGetLastError();
+}
+#endif
+
+static size_t GPC_KNAME(v_smem_bytes)(int nmax) {
+#if defined(GPC_SMALL_ONLY)
+    const int n = nmax < 1 ? 1 : (nmax > GPC_SMALL_NMAX ? GPC_SMALL_NMAX : nmax);
+    return GPC_SMALL_ARENA_OFF + GPC_SMALL_VEC_BYTES(n) + small_arena_bytes(n);
+#else
+    (void)nmax;
+    return eval_smem_bytes() + sizeof(OptSmem);
+#endif
+}
 
 static int GPC_KNAME(v_upload_constants)(const double* z, const double* w) {
     if (cudaMemcpyToSymbol(c_gh_z, z, sizeof(double) * GPC_NGH) != cudaSuccess) return -1;
     if (cudaMemcpyToSymbol(c_gh_w, w, sizeof(double) * GPC_NGH) != cudaSuccess) return -1;
-    const int sb = (int)GPC_KNAME(v_smem_bytes)();
-    cudaFuncSetAttribute(GPC_KNAME(k_fit), cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-    cudaFuncSetAttribute(GPC_KNAME(k_elbo_grad), cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+    const int sb = (int)GPC_KNAME(v_smem_bytes)(GPC_SMALL_NMAX_OR_0);
+    if (cudaFuncSetAttribute(GPC_KNAME(k_fit), cudaFuncAttributeMaxDynamicSharedMemorySize, sb) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(GPC_KNAME(k_elbo_grad), cudaFuncAttributeMaxDynamicSharedMemorySize, sb) != cudaSuccess) return -1;
+#if !defined(GPC_FUSED_ONLY) && !defined(GPC_SMALL_ONLY)
+    if (cudaFuncSetAttribute(GPC_KNAME(k_predict), cudaFuncAttributeMaxDynamicSharedMemorySize, sb) != cudaSuccess) return -1;
+#endif
     return 0;
 }
 
-static int GPC_KNAME(v_occupancy)() {
+static int GPC_KNAME(v_occupancy)(int nmax) {
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, GPC_KNAME(k_fit), GPC_THREADS, GPC_KNAME(v_smem_bytes)());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, GPC_KNAME(k_fit), GPC_THREADS, GPC_KNAME(v_smem_bytes)(nmax));
     return per_sm;
 }
 
-static cudaError_t GPC_KNAME(v_launch_fit)(const void* a, int grid, cudaStream_t s) {
-    GPC_KNAME(k_fit)<<<grid, GPC_THREADS, GPC_KNAME(v_smem_bytes)(), s>>>(*static_cast<const FitArgs*>(a));
+static cudaError_t GPC_KNAME(v_launch_fit)(const void* a, int grid, int nmax, cudaStream_t s) {
+    GPC_KNAME(k_fit)<<<grid, GPC_THREADS, GPC_KNAME(v_smem_bytes)(nmax), s>>>(*static_cast<const FitArgs*>(a));
     return cudaGetLastError();
 }
 
-static cudaError_t GPC_KNAME(v_launch_eval)(const void* a, int grid, cudaStream_t s) {
-    GPC_KNAME(k_elbo_grad)<<<grid, GPC_THREADS, GPC_KNAME(v_smem_bytes)(), s>>>(*static_cast<const EvalArgs*>(a));
+static cudaError_t GPC_KNAME(v_launch_eval)(const void* a, int grid, int nmax, cudaStream_t s) {
+    GPC_KNAME(k_elbo_grad)<<<grid, GPC_THREADS, GPC_KNAME(v_smem_bytes)(nmax), s>>>(*static_cast<const EvalArgs*>(a));
     return cudaGetLastError();
 }
 
-#if defined(GPC_PHASE_PROF) && !defined(GPC_DENSE_ONLY)
+#if defined(GPC_PHASE_PROF) && !defined(GPC_DENSE_ONLY) && !defined(GPC_SMALL_ONLY)
 static int GPC_KNAME(v_read_prof)(unsigned long long* out16) {
     cudaDeviceSynchronize();
     if (cudaMemcpyFromSymbol(out16, g_phase_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
@@ -348,7 +522,11 @@ VariantOps GPC_KNAME(gpc_variant_ops)() {
     o.launch_fit = GPC_KNAME(v_launch_fit);
     o.launch_eval = GPC_KNAME(v_launch_eval);
     o.read_prof = nullptr;
-#if defined(GPC_PHASE_PROF) && !defined(GPC_DENSE_ONLY)
+    o.launch_predict = nullptr;
+#if !defined(GPC_FUSED_ONLY) && !defined(GPC_SMALL_ONLY)
+    o.launch_predict = GPC_KNAME(v_launch_predict);
+#endif
+#if defined(GPC_PHASE_PROF) && !defined(GPC_DENSE_ONLY) && !defined(GPC_SMALL_ONLY)
     o.read_prof = GPC_KNAME(v_read_prof);
 #endif
     return o;

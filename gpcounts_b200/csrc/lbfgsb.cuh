@@ -15,7 +15,12 @@
 // All scalar logic is executed redundantly by every thread on CTA-uniform values.
 #pragma once
 #include "model.cuh"
+#include "fastmath.cuh"
+#ifdef GPC_SMALL_ONLY
+#include "vgp_small.cuh"
+#else
 #include "svgp_fused.cuh"
+#endif
 
 #define GPC_MMAX 10
 #define GPC_EPSMCH 2.220446049250313e-16
@@ -33,6 +38,7 @@ struct OptSmem {
     double T[GPC_MMAX][GPC_MMAX];      // formt scratch
     int info;
     int info_dir;                      // outcome of the direction solve (formk / subsm) done at the end of an iteration
+    double red[64];                    // CTA reduction scratch of the optimiser
 };
 
 struct DcsrchState {
@@ -288,6 +294,130 @@ __device__ void subsm_solve(OptSmem* os, int col) {
     __syncwarp();
 }
 
+// ---- register versions of formk / subsm / formt ------------------------------------------------------------------------
+// The 2m x 2m middle matrix lives in the registers of ONE warp, lane j holding column j of the upper-triangular factor
+// (c[i] = U[i][j], i <= j); pivots and row entries travel by shuffle, square roots / divisions are branch-free
+// (gpc_rsqrt, gpc_rcp).  Blocks sit at fixed offsets (block 1 = rows / columns 0..9, block 2 = 10..19) and unused rows are
+// identity, so every register index is a compile-time constant whatever `col` is.  The arithmetic is the right-looking
+// elimination of warp_chol_upper / formk_free above (same order of the updates); ~2 us instead of ~25 us per iteration.
+
+// In-place upper Cholesky (LEL^T form when SPLIT: block-2 rows accumulate + instead of - while k runs over block 1).
+// Returns 0 or the 1-based index of the first non-positive pivot (warp-uniform).
+template <int NN, bool SPLIT>
+__device__ __forceinline__ int warp_chol_cols(double (&c)[NN]) {
+    const unsigned FULL = 0xffffffffu;
+    int info = 0;
+#pragma unroll
+    for (int k = 0; k < NN; ++k) {
+        const double piv = __shfl_sync(FULL, c[k], k);
+        if (!(piv > 0.0) && info == 0) info = k + 1;
+        const double rinv = gpc_rsqrt(piv);
+        double sq = piv * rinv;
+        sq = fma(fma(-sq, sq, piv), 0.5 * rinv, sq);
+        const int lane = threadIdx.x & 31;
+        const double ukj = (lane == k) ? sq : c[k] * rinv;          // my entry of row k (valid for lane >= k)
+        c[k] = ukj;
+#pragma unroll
+        for (int i = k + 1; i < NN; ++i) {
+            const double uki = __shfl_sync(FULL, ukj, i);
+            if (SPLIT && k < NN / 2 && i >= NN / 2) c[i] = fma(uki, ukj, c[i]);
+            else c[i] = fma(-uki, ukj, c[i]);
+        }
+    }
+    return info;
+}
+
+// formk (all variables free) + subsm on one warp.  `updated`: the memory changed since the last call (else the factor kept
+// in os->WN is reused).  On success os->wv holds K^-1 wv in the layout the direction pass expects.  Returns 0 / -1 / -2.
+__device__ __forceinline__ int formk_subsm_reg(OptSmem* os, int col, double theta, bool updated) {
+    const unsigned FULL = 0xffffffffu;
+    constexpr int H = GPC_MMAX, NN = 2 * GPC_MMAX;
+    const int lane = threadIdx.x & 31;
+    double* WN = &os->WN[0][0];
+    double c[NN];
+    int info = 0;
+    if (updated) {
+        // column `lane` of [Y'Y / theta + D, R_z'; . , 0] (upper part), identity on unused rows / columns
+        const int jb = lane < H ? lane : lane - H;                  // index within the block
+        const bool jact = lane < NN && jb < col;
+#pragma unroll
+        for (int i = 0; i < NN; ++i) {
+            const int ib = i < H ? i : i - H;
+            double v = (i == lane) ? 1.0 : 0.0;                     // identity on unused rows / columns
+            if (jact && ib < col) {
+                if (i < H && lane < H) v = (i <= lane) ? os->YY[lane][i] / theta + (i == lane ? os->SY[i][i] : 0.0) : 0.0;
+                else if (i < H) v = (ib >= jb) ? os->RZ[jb][ib] : 0.0;     // block (1,2) = R_z': [i][j] = s_j . y_i, j <= i
+                else v = 0.0;                                        // block (2,2) starts at zero, diagonal included
+            }
+            c[i] = v;
+        }
+        // an active block-2 column starts from zero on its diagonal (theta S'AA'S = 0): the + updates of block 1 fill it
+        info = warp_chol_cols<NN, true>(c);
+        if (info != 0) return info <= H ? -1 : -2;
+        if (lane < NN) {
+#pragma unroll
+            for (int i = 0; i < NN; ++i) WN[i * NN + lane] = c[i];
+        }
+        __syncwarp();
+    } else {
+#pragma unroll
+        for (int i = 0; i < NN; ++i) c[i] = (lane < NN) ? WN[i * NN + lane] : ((i == lane) ? 1.0 : 0.0);
+    }
+    // wv = [Y'r ; theta S'r] with r = -g, blocks at fixed offsets
+    double b = 0.0;
+    if (lane < col) b = -os->dots[lane][5];
+    else if (lane >= H && lane - H < col) b = -theta * os->dots[lane - H][4];
+    // own diagonal reciprocal
+    double dg = 1.0;
+#pragma unroll
+    for (int i = 0; i < NN; ++i) if (i == lane) dg = c[i];
+    const double dinv = gpc_rcp(dg);
+    // U^T x = b  (forward; lane i owns column i of U = row i of U^T)
+#pragma unroll
+    for (int k = 0; k < NN; ++k) {
+        const double xk = __shfl_sync(FULL, b * dinv, k);
+        b = (lane == k) ? xk : ((lane > k) ? fma(-c[k], xk, b) : b);
+    }
+    if (lane < H) b = -b;
+    // U x = b  (backward; needs rows: lane i reads row i of the factor from shared memory)
+    double u[NN];
+#pragma unroll
+    for (int j = 0; j < NN; ++j) u[j] = (lane < NN) ? WN[lane * NN + j] : 0.0;
+#pragma unroll
+    for (int k = NN - 1; k >= 0; --k) {
+        const double xk = __shfl_sync(FULL, b * dinv, k);
+        b = (lane == k) ? xk : ((lane < k) ? fma(-u[k], xk, b) : b);
+    }
+    if (lane < col) os->wv[lane] = b;
+    else if (lane >= H && lane - H < col) os->wv[col + lane - H] = b;
+    return 0;
+}
+
+// formt: T = theta SS + L D^-1 L^T positive definite?  0 on success (one warp, registers).
+__device__ __forceinline__ int formt_check_reg(OptSmem* os, int col, double theta) {
+    const unsigned FULL = 0xffffffffu;
+    constexpr int H = GPC_MMAX;
+    const int lane = threadIdx.x & 31;
+    const double dmine = (lane < col) ? gpc_rcp(os->SY[lane][lane]) : 0.0;
+    double dk[H];
+#pragma unroll
+    for (int k = 0; k < H; ++k) dk[k] = __shfl_sync(FULL, dmine, k);       // 1 / SY[k][k]
+    double c[H];
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        double v = (i == lane) ? 1.0 : 0.0;
+        if (lane < col && i <= lane) {
+            double ddum = 0.0;
+#pragma unroll
+            for (int k = 0; k < H; ++k)
+                if (k < i) ddum = fma(os->SY[i][k] * os->SY[lane][k], dk[k], ddum);
+            v = ddum + theta * os->SS[i][lane];
+        }
+        c[i] = v;
+    }
+    return warp_chol_cols<H, false>(c);
+}
+
 struct OptResult {
     int task;          // TASK_*
     int nit, nfev;
@@ -371,11 +501,11 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
     double f;
     if (eval_loss(md, Z, y, scale, ws, sm, f, res.eval_cycles) != GPC_ST_OK) { res.task = TASK_CHOL; res.nfev = 1; return res; }
     int nfev = 1, nit = 0;
-    trace_eval(tr, f, 0.0, 0.0, ws.x, ws.g, P, sm->red);
+    trace_eval(tr, f, 0.0, 0.0, ws.x, ws.g, P, os->red);
     // g <- -grad(ELBO)
     double gmax = 0.0;
     for (int i = tid; i < P; i += GPC_THREADS) { const double v = -ws.g[i]; ws.g[i] = v; gmax = fmax(gmax, fabs(v)); }
-    double sbgnrm = cta_max(gmax, sm->red);
+    double sbgnrm = cta_max(gmax, os->red);
     if (sbgnrm <= opt.gtol) { res.task = TASK_PGTOL; res.nfev = nfev; res.f = f; res.gnorm = sbgnrm; return res; }
     int col = 0, head = 0;
     double theta = 1.0;
@@ -448,7 +578,7 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
                 }
             }
         }
-        cta_sum_n<2>(acc2, sm->red);
+        cta_sum_n<2>(acc2, os->red);
         // ------------------------------------------------------------------ line search (lnsrlb)
         const double dtd = acc2[0];
         const double dnorm = sqrt(dtd);
@@ -481,17 +611,33 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
                 // one pass: g <- -grad, g.d, max|g|, |g - gold|^2
                 double a3[2] = {0.0, 0.0};
                 double mx = 0.0;
-                for (int i = tid; i < P; i += GPC_THREADS) {
-                    const double v = -ws.g[i];
-                    ws.g[i] = v;
-                    a3[0] = fma(v, ws.d[i], a3[0]);
-                    const double r = v - ws.gold[i];
-                    a3[1] = fma(r, r, a3[1]);
-                    mx = fmax(mx, fabs(v));
+                // four elements per thread at a time: the twelve loads are independent (one L2 round trip instead of four);
+                // the per-element arithmetic and the order of the partial sums are unchanged
+                for (int i0 = tid; i0 < P; i0 += 4 * GPC_THREADS) {
+                    double gv[4], dv[4], ov[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * GPC_THREADS;
+                        gv[u] = i < P ? ws.g[i] : 0.0;
+                        dv[u] = i < P ? ws.d[i] : 0.0;
+                        ov[u] = i < P ? ws.gold[i] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * GPC_THREADS;
+                        if (i < P) {
+                            const double v = -gv[u];
+                            ws.g[i] = v;
+                            a3[0] = fma(v, dv[u], a3[0]);
+                            const double r = v - ov[u];
+                            a3[1] = fma(r, r, a3[1]);
+                            mx = fmax(mx, fabs(v));
+                        }
+                    }
                 }
-                cta_sum2_max(a3[0], a3[1], mx, sm->red);
+                cta_sum2_max(a3[0], a3[1], mx, os->red);
                 gd = a3[0]; rr = a3[1]; gmax = mx;
-                trace_eval(tr, f, stp, gd, ws.x, ws.g, P, sm->red);
+                trace_eval(tr, f, stp, gd, ws.x, ws.g, P, os->red);
                 const int t = dcsrch_step(ls, f, gd);
                 if (t != 0) break;
                 if (ifun >= opt.maxls) { ls_failed = true; break; }
@@ -526,26 +672,49 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
             if (col == m) {       // drop the oldest pair: shift the small matrices
                 __syncthreads();
                 {
-                    // one element per thread: read (i + 1, j + 1), barrier, write (i, j)
-                    const int i = tid / GPC_MMAX, j = tid % GPC_MMAX;
-                    const bool mine = i < m - 1 && j < m - 1;
-                    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-                    if (mine) { v0 = os->SS[i + 1][j + 1]; v1 = os->SY[i + 1][j + 1]; v2 = os->YY[i + 1][j + 1]; v3 = os->RZ[i + 1][j + 1]; }
+                    // read (i + 1, j + 1), barrier, write (i, j): (m - 1)^2 <= 81 elements, at most two per thread
+                    constexpr int NP = (81 + GPC_THREADS - 1) / GPC_THREADS;
+                    double v0[NP], v1[NP], v2[NP], v3[NP];
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        const int e = tid + q * GPC_THREADS, i = e / GPC_MMAX, j = e % GPC_MMAX;
+                        const bool mine = i < m - 1 && j < m - 1;
+                        v0[q] = v1[q] = v2[q] = v3[q] = 0.0;
+                        if (mine) { v0[q] = os->SS[i + 1][j + 1]; v1[q] = os->SY[i + 1][j + 1]; v2[q] = os->YY[i + 1][j + 1]; v3[q] = os->RZ[i + 1][j + 1]; }
+                    }
                     __syncthreads();
-                    if (mine) { os->SS[i][j] = v0; os->SY[i][j] = v1; os->YY[i][j] = v2; os->RZ[i][j] = v3; }
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        const int e = tid + q * GPC_THREADS, i = e / GPC_MMAX, j = e % GPC_MMAX;
+                        if (i < m - 1 && j < m - 1) { os->SS[i][j] = v0[q]; os->SY[i][j] = v1[q]; os->YY[i][j] = v2[q]; os->RZ[i][j] = v3[q]; }
+                    }
                 }
                 head = (head + 1) % m;
                 col = m - 1;
             }
             // one pass: s = stp * d, y = g - gold, stored in the memory and kept in (d, gold) for the dot products
             const size_t slot = (size_t)((head + col) % m) * P;
-            for (int i = tid; i < P; i += GPC_THREADS) {
-                const double si = (stp == 1.0) ? ws.d[i] : ws.d[i] * stp;
-                const double yi = ws.g[i] - ws.gold[i];
-                ws.d[i] = si;
-                ws.gold[i] = yi;
-                ws.WS[slot + i] = si;
-                ws.WY[slot + i] = yi;
+            for (int i0 = tid; i0 < P; i0 += 4 * GPC_THREADS) {
+                double dv[4], gv[4], ov[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * GPC_THREADS;
+                    dv[u] = i < P ? ws.d[i] : 0.0;
+                    gv[u] = i < P ? ws.g[i] : 0.0;
+                    ov[u] = i < P ? ws.gold[i] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * GPC_THREADS;
+                    if (i < P) {
+                        const double si = (stp == 1.0) ? dv[u] : dv[u] * stp;
+                        const double yi = gv[u] - ov[u];
+                        ws.d[i] = si;
+                        ws.gold[i] = yi;
+                        ws.WS[slot + i] = si;
+                        ws.WY[slot + i] = yi;
+                    }
+                }
             }
             ++col;
             theta = rr / dr;
@@ -556,12 +725,23 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
         for (int j = warp; j < col; j += GPC_THREADS / 32) {
             const size_t slot = (size_t)((head + j) % m) * P;
             double a[6] = {0, 0, 0, 0, 0, 0};
-            for (int i = lane; i < P; i += 32) {
-                const double s = ws.WS[slot + i], yv = ws.WY[slot + i];
-                const double di = ws.d[i], ri = ws.gold[i], gi = ws.g[i];
-                a[0] = fma(s, di, a[0]); a[1] = fma(yv, di, a[1]);
-                a[2] = fma(s, ri, a[2]); a[3] = fma(yv, ri, a[3]);
-                a[4] = fma(s, gi, a[4]); a[5] = fma(yv, gi, a[5]);
+            for (int i0 = lane; i0 < P; i0 += 4 * 32) {           // twenty independent loads per step, same summation order
+                double sv[4], yv[4], dv[4], rv[4], gv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * 32;
+                    const bool in = i < P;
+                    sv[u] = in ? ws.WS[slot + i] : 0.0; yv[u] = in ? ws.WY[slot + i] : 0.0;
+                    dv[u] = in ? ws.d[i] : 0.0; rv[u] = in ? ws.gold[i] : 0.0; gv[u] = in ? ws.g[i] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (i0 + u * 32 < P) {
+                        a[0] = fma(sv[u], dv[u], a[0]); a[1] = fma(yv[u], dv[u], a[1]);
+                        a[2] = fma(sv[u], rv[u], a[2]); a[3] = fma(yv[u], rv[u], a[3]);
+                        a[4] = fma(sv[u], gv[u], a[4]); a[5] = fma(yv[u], gv[u], a[5]);
+                    }
+                }
             }
 #pragma unroll
             for (int q = 0; q < 6; ++q) a[q] = warp_sum(a[q]);
@@ -588,20 +768,11 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
         // formt (acceptance of the new pair) on warp 0 and, concurrently on warp 1, the direction solve of the next
         // iteration: formk (only when a pair was stored) and subsm with the dot products of the new gradient
         if (!skip && warp == 0) {
-            const int info = formt_check(os, col, theta);
+            const int info = formt_check_reg(os, col, theta);
             if (lane == 0) os->info = info;
         }
         if (warp == 1 && col > 0) {
-            int info = 0;
-            if (updated) info = formk_free(os, col, theta);
-            if (info == 0) {
-                if (lane < col) {
-                    os->wv[lane] = -os->dots[lane][5];                 // Y_j . r, r = -g
-                    os->wv[col + lane] = -theta * os->dots[lane][4];   // theta * S_j . r
-                }
-                __syncwarp();
-                subsm_solve(os, col);
-            }
+            const int info = formk_subsm_reg(os, col, theta, updated);
             if (lane == 0) os->info_dir = info;
         }
         __syncthreads();

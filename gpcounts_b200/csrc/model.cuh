@@ -28,6 +28,15 @@ struct SlotWs {
     double *Kuf, *A, *B, *S;                      // M x N   (sparse models)
     double *v0, *v1, *v2, *v3;                    // N
     double *x, *g, *d, *xold, *gold, *z, *WS, *WY;   // optimiser vectors (P) and memory (m x P)
+    // TMA descriptors (CUtensorMap in kernel-parameter space) of the gene-major count / scale matrices and the row of the
+    // gene being evaluated, or nullptr: then the evaluators read y / scale through their pointer arguments
+    const void *tmY, *tmS;
+    int row;
+    // 1 on the first evaluation of a fit attempt (set by the callers, cleared by the evaluator): a model whose kernel
+    // hyper-parameters are frozen (branching grid, train_mask & 3 == 0 - GPcounts_Module.py:608-614) builds and factors its
+    // Gram matrix then and reuses the factor in ws.L for every further evaluation of the attempt
+    int fresh;
+    int arena_off;      // small instantiation: byte offset of the evaluator's arena in the dynamic shared memory
 };
 
 struct KernParams {
@@ -199,8 +208,13 @@ __device__ __noinline__ int eval_vgp(const ModelDev& md, const double* y, const 
     double* fmean = ws.v0; double* fvar = ws.v1; double* gm = ws.v2; double* gv = ws.v3;
 
     const double shift = md.jitter + (md.kernel == GPC_BRANCH ? GPC_BRANCH_NOISE : 0.0);
-    build_gram_square(kp, N, md.X, shift, ws.K0, ws.L);
-    if (!cta_potrf(N, ws.L, N, ws.dinv, sm)) return GPC_ST_CHOL;
+    const bool need_kernel_grad = (md.train_mask & 3) != 0;
+    if (need_kernel_grad || ws.fresh) {            // frozen kernel: the factor of the first evaluation stays in ws.L
+        build_gram_square(kp, N, md.X, shift, ws.K0, ws.L);
+        if (!cta_potrf(N, ws.L, N, ws.dinv, sm)) return GPC_ST_CHOL;
+    }
+    __syncthreads();
+    if (tid == 0) const_cast<SlotWs&>(ws).fresh = 0;
     unpack_lq(N, lq_packed, ws.Lq);
     // C = L * Lq (lower)
     cta_gemm<false, false>(N, N, N, 1.0, ws.L, N, ws.Lq, N, 0.0, ws.G1, N, F_A_LOWER | F_B_LOWER | F_C_LOWER, sm);
@@ -246,7 +260,6 @@ __device__ __noinline__ int eval_vgp(const ModelDev& md, const double* y, const 
     __syncthreads();
     const double kl = kl_white(N, q_mu, lq_packed, sm);
     double gvar = 0.0, gls = 0.0;
-    const bool need_kernel_grad = (md.train_mask & 3) != 0;
     if (need_kernel_grad) {
         cta_chol_backward(N, ws.L, N, ws.dinv, ws.G2, N, ws.G3, N, sm);
         gram_square_grad(kp, N, md.X, ws.K0, ws.G2, gvar, gls, sm);
@@ -506,9 +519,17 @@ __device__ __forceinline__ bool use_fused(const ModelDev& md) {
     return md.kind == GPC_SVGP && md.M <= 64 && md.d <= 2 && md.kernel != GPC_BRANCH;
 }
 
+#define GPC_SMALL_ARENA_OFF 8704     // small instantiation: [OptSmem | optimiser vectors | arena of eval_vgp_small]
+#define GPC_SMALL_PVEC(n) ((((size_t)(4 + (n) + (n) * ((n) + 1) / 2) + 15) & ~(size_t)15))   // padded parameter count
+#define GPC_SMALL_VEC_BYTES(n) (6 * GPC_SMALL_PVEC(n) * sizeof(double))
+__device__ __noinline__ int eval_vgp_small(const ModelDev& md, const double* y, const double* scale, const double* theta,
+                                           double* grad, double* f_out, unsigned char* arena);
+
 __device__ __noinline__ int model_eval_direct(const ModelDev& md, const double* Z, const double* y, const double* scale,
                           const double* theta, double* grad, double* f_out, const SlotWs& ws, CtaSmem* sm) {
-#ifdef GPC_FUSED_ONLY
+#if defined(GPC_SMALL_ONLY)
+    return eval_vgp_small(md, y, scale, theta, grad, f_out, g_smem + ws.arena_off);
+#elif defined(GPC_FUSED_ONLY)
     return eval_svgp_fused(md, Z, y, scale, theta, grad, f_out, ws, reinterpret_cast<FusedSmem*>(sm));
 #else
 #ifndef GPC_DENSE_ONLY

@@ -31,14 +31,22 @@ static_assert(FZ_WPR == 1, "the fused evaluator is written for 8 warps (256 thre
 // thread 0 accumulates SM-clock deltas between phase boundaries of every evaluation into g_phase_prof.
 #ifdef GPC_PHASE_PROF
 __device__ unsigned long long g_phase_prof[16];
-#define PROF_DECL long long prof_t = clock64(); long long prof_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define PROF_DECL long long prof_t = clock64(); long long prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
 #define PROF_MARK(k) do { const long long t_ = clock64(); prof_acc[k] += t_ - prof_t; prof_t = t_; } while (0)
-#define PROF_FLUSH do { if (threadIdx.x == 0) { for (int q_ = 0; q_ < 10; ++q_) atomicAdd(&g_phase_prof[q_], (unsigned long long)prof_acc[q_]); atomicAdd(&g_phase_prof[15], 1ull); } } while (0)
+#define PROF_FLUSH do { if (threadIdx.x == 0) { for (int q_ = 0; q_ < 12; ++q_) atomicAdd(&g_phase_prof[q_], (unsigned long long)prof_acc[q_]); atomicAdd(&g_phase_prof[15], 1ull); } } while (0)
 #else
 #define PROF_DECL
 #define PROF_MARK(k)
 #define PROF_FLUSH
 #endif
+
+// Per-evaluation constants of the tile loop.  `md` and `ws` arrive as generic references (ABI call), so every use after a
+// barrier is a generic load or a local-memory reload of a spilled copy; one copy in shared memory makes them plain LDS.
+struct FzCfg {
+    int kernel, lik, n_off, row;
+    const double* X;
+    const void *tmY, *tmS;
+};
 
 struct FusedSmem {
     double T0[FZ_MAT];              // Kuf tile            (end phase: Lq)
@@ -49,12 +57,17 @@ struct FusedSmem {
     double W[FZ_MAT];               // Lq Lq^T - I (symmetric)
     double qmu[64];
     double gq[2 * FZ_WPR][64];      // A g_m accumulators, one per column group of a tile (deterministic sums)
-    double col[8][64];              // per column: -, -, gm, -, y, scale, 2*gv; [7] = u = Lm^-T q_mu (per row)
+    double gm[64], gv2[64];         // per column of the current tile: d VE / d fmean, 2 d VE / d fvar
+    double uvec[64];                // u = Lm^-T q_mu (per row)
+    alignas(128) double ytile[2][64];   // counts of the current / next column tile   (TMA destinations, double-buffered)
+    alignas(128) double stile[2][64];   // scale factors likewise
+    unsigned long long mbar[2];     // transaction barriers of the two tile buffers
     double red[64];
     double red2[80];                // reduction scratch for up to 10 sums (cta_sum_n<K> uses K x 8 doubles)
     int chol_ok;                    // blocked Cholesky: all pivots positive so far
     double Zs[64 * 2];              // inducing inputs (d <= 2)
-    double Xs[64 * 2];              // inputs of the current column tile
+    double Xs[2][64 * 2];           // inputs of the current / next column tile
+    FzCfg cfg;
     KernParams kp;                  // per-evaluation constants live here rather than in registers: the evaluator
     LikParams lp;                   // is register-bound (rank-update accumulators), reloads from smem are cheap
 };
@@ -62,6 +75,30 @@ struct FusedSmem {
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// ---- TMA (cp.async.bulk.tensor, SASS UTMALDG) + mbarrier helpers for the y / scale tile stream ---------------------
+__device__ __forceinline__ unsigned fz_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fz_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(fz_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fz_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(fz_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fz_mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "FZ_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra FZ_DONE;\n"
+                 "bra FZ_WAIT;\n"
+                 "FZ_DONE:\n"
+                 "}" :: "r"(fz_smem_u32(bar)), "r"(parity) : "memory");
+}
+// one 64-column x 1-row box of a [D][ld] FP64 tensor -> shared memory, completion signalled on `bar`
+__device__ __forceinline__ void fz_tma_row_tile(void* dst, const void* tmap, int col, int row, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(fz_smem_u32(dst)), "l"(tmap), "r"(col), "r"(row), "r"(fz_smem_u32(bar)) : "memory");
 }
 
 // Warp-level product on smem operands: for column tiles ct in [ct0, ct1):
@@ -148,18 +185,6 @@ __device__ __forceinline__ void acc_store(const double (&acc)[8][2], double* C, 
     for (int ct = 0; ct < 8; ++ct)
         if (ct >= ct0 && ct < ct1)
             *reinterpret_cast<double2*>(&C[(r0 + ar) * FZ_LD + ct * 8 + ac]) = make_double2(acc[ct][0], acc[ct][1]);
-}
-
-// x^-1/2 without a slow-path branch: hardware seed (MUFU.RSQ64H) + two third-order Newton steps.
-__device__ __forceinline__ double gpc_rsqrt(double x) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {                       // third-order steps: 20 -> 60 -> 180 bits
-        const double e = fma(-x * y, y, 1.0);
-        y = fma(y * e, fma(0.375, e, 0.5), y);
-    }
-    return y;
 }
 
 // One 8 x 8 tile product on the FP64 tensor pipe, operands in shared memory (ld FZ_LD):
@@ -334,6 +359,8 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
         const Hyper h0 = hyper_from_theta(md, theta);
         kern_setup(fs->kp, md, h0.var, h0.ls);
         lik_setup(fs->lp, md.lik, h0.alpha, h0.km);
+        fs->cfg.kernel = md.kernel; fs->cfg.lik = md.lik; fs->cfg.n_off = md.n_off; fs->cfg.row = ws.row;
+        fs->cfg.X = md.X; fs->cfg.tmY = ws.tmY; fs->cfg.tmS = ws.tmS;
     }
     __syncthreads();
     const KernParams& kp = fs->kp;
@@ -493,7 +520,7 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
     if (tid < 64) {                                                 // u = Linv^T q_mu
         double u = 0.0;
         for (int k = tid; k < Mp; ++k) u = fma(fs->Linv[k * FZ_LD + tid], fs->qmu[k], u);
-        fs->col[7][tid] = u;
+        fs->uvec[tid] = u;
     }
 
     // ---- column tiles -------------------------------------------------------------------------------------------
@@ -518,17 +545,48 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
     accT_zero<4>(accHB);
     const int ar = lane >> 2, ac = 2 * (lane & 3);
     PROF_MARK(3);
-    for (int n0 = 0; n0 < N; n0 += 64) {
-        const int nt = min(64, N - n0);
-        __syncthreads();
-        if (tid < 64 * dd) fs->Xs[tid] = (tid < nt * dd) ? md.X[(size_t)n0 * dd + tid] : 0.0;
-        if (tid >= 128 && tid < 192) {
+    // Tile stream: the counts / scale factors of column tile t+1 travel by TMA (one 64 x 1 box of the gene-major [D][ldy]
+    // tensors per tile, double-buffered, mbarrier completion) while tile t is processed; the inputs X of tile t+1 are
+    // prefetched into registers.  Without descriptors (odd row pitch) y / scale are read with ordinary loads.
+    const FzCfg& cf = fs->cfg;
+    const bool tma = cf.tmY != nullptr;
+    const bool has_scale = scale != nullptr;
+    if (tma && tid == 0) {
+        fz_mbar_init(&fs->mbar[0], 1);
+        fz_mbar_init(&fs->mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    double xpre = 0.0;
+    if (tid < 64 * dd) xpre = (tid < min(64, N) * dd) ? cf.X[tid] : 0.0;
+    __syncthreads();
+    if (tma && tid == 0) {
+        fz_mbar_expect_tx(&fs->mbar[0], has_scale ? 1024u : 512u);
+        fz_tma_row_tile(fs->ytile[0], cf.tmY, cf.n_off, cf.row, &fs->mbar[0]);
+        if (has_scale) fz_tma_row_tile(fs->stile[0], cf.tmS, cf.n_off, cf.row, &fs->mbar[0]);
+    }
+    if (tid < 64 * dd) fs->Xs[0][tid] = xpre;
+    int it = 0;
+    for (int n0 = 0; n0 < N; n0 += 64, ++it) {
+        const int nt = min(64, N - n0), bf = it & 1;
+        __syncthreads();                                   // tile it-1 is finished everywhere: its buffers may be refilled
+        const bool more = n0 + 64 < N;
+        if (more) {
+            if (tma && tid == 0) {
+                fz_mbar_expect_tx(&fs->mbar[bf ^ 1], has_scale ? 1024u : 512u);
+                fz_tma_row_tile(fs->ytile[bf ^ 1], cf.tmY, cf.n_off + n0 + 64, cf.row, &fs->mbar[bf ^ 1]);
+                if (has_scale) fz_tma_row_tile(fs->stile[bf ^ 1], cf.tmS, cf.n_off + n0 + 64, cf.row, &fs->mbar[bf ^ 1]);
+            }
+            const int ntn = min(64, N - n0 - 64);
+            if (tid < 64 * dd) xpre = (tid < ntn * dd) ? cf.X[(size_t)(n0 + 64) * dd + tid] : 0.0;   // consumed at the end of the tile
+        }
+        if (!tma && tid >= 128 && tid < 192) {
             const int c = tid - 128;
             const bool v = c < nt;
-            fs->col[4][c] = v ? y[n0 + c] : 0.0;
-            fs->col[5][c] = (v && scale) ? scale[n0 + c] : 1.0;
+            fs->ytile[bf][c] = v ? y[n0 + c] : 0.0;
+            fs->stile[bf][c] = (v && has_scale) ? scale[n0 + c] : 1.0;
         }
-        __syncthreads();
+        const double* Xcur = fs->Xs[bf];
         // ---- Kuf tile: thread owns column c = tid & 63, rows (tid >> 6) + FZ_LPC t ---------------------------------
         // The FZ_RPT squared distances of a thread go through one vectorised exp (independent chains, fastmath.cuh);
         // padded rows / columns (Zs, Xs are zero there) are computed too and masked on the way out.
@@ -536,14 +594,14 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
             const int c = tid & 63, ib = tid >> 6;
             const bool cv = c < nt;
             const double var = kp.var;
-            if (md.kernel == GPC_CONST) {
+            if (cf.kernel == GPC_CONST) {
 #pragma unroll
                 for (int t = 0; t < FZ_RPT; ++t) {
                     const int i = ib + FZ_LPC * t;
                     fs->T0[i * FZ_LD + c] = (cv && i < M) ? var : 0.0;
                 }
             } else {
-                const double* xc = fs->Xs + c * dd;
+                const double* xc = Xcur + c * dd;
                 const double x0 = xc[0], x1 = dd > 1 ? xc[1] : 0.0;
                 const double ce = -0.5 * kp.inv_ls2;
                 double r2[FZ_RPT], ev[FZ_RPT];
@@ -591,6 +649,7 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
         PROF_MARK(6);
         // ---- per-column statistics + quadrature: FZ_LPC adjacent lanes per column ---------------------------------
         //   fmean = a . q_mu,  fvar = kdiag + a . (W a)
+        if (tma) fz_mbar_wait(&fs->mbar[bf], (unsigned)(it >> 1) & 1u);      // y / scale of this tile have landed
         {
             const int c = tid / FZ_LPC, part = tid % FZ_LPC;
             double s1 = 0.0, s2 = 0.0;
@@ -608,11 +667,11 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
                 s1 += __shfl_xor_sync(0xffffffffu, s1, o);
                 s2 += __shfl_xor_sync(0xffffffffu, s2, o);
             }
-            const double fm = s1, fv = kdiag + s2, yy = fs->col[4][c];
+            const double fm = s1, fv = kdiag + s2, yy = fs->ytile[bf][c];
             double ve = 0.0, gm = 0.0, gz = 0.0, da = 0.0, dk = 0.0;
             bool poison = false;
             if (c < nt) {
-                if (md.lik == GPC_POISSON) {
+                if (cf.lik == GPC_POISSON) {
                     if (part == 0) {
                         const double e = exp(fm + 0.5 * fv);
                         ve = yy * fm - e - lgamma(yy + 1.0);
@@ -621,7 +680,7 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
                     }
                 } else {
                     const double sd = sqrt(fv);
-                    const LikPart o = (md.lik == GPC_NB) ? lik_nodes_nb<FZ_LPC>(lp, fm, sd, yy, fs->col[5][c], part)
+                    const LikPart o = (cf.lik == GPC_NB) ? lik_nodes_nb<FZ_LPC>(lp, fm, sd, yy, has_scale ? fs->stile[bf][c] : 1.0, part)
                                                          : lik_nodes<FZ_LPC>(lp, fm, sd, yy, 0.0, part);
                     ve = o.ve; gm = o.gm; gz = o.gz; da = o.da; dk = o.dk; poison = o.poison;
                 }
@@ -635,10 +694,10 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
             }
             if (part == 0) {
                 double gv = 0.0;
-                if (c < nt) gv = (md.lik == GPC_POISSON) ? gz : gz / (2.0 * sqrt(fv));
+                if (c < nt) gv = (cf.lik == GPC_POISSON) ? gz : gz / (2.0 * sqrt(fv));
                 else gm = 0.0;
-                fs->col[2][c] = gm;
-                fs->col[6][c] = 2.0 * gv;
+                fs->gm[c] = gm;
+                fs->gv2[c] = 2.0 * gv;
                 sum_gv += gv;
                 // <Abar, A> = sum_n g_m fmean + 2 g_v a.(W a)   (= <S, Kuf>: d/d variance of the cross-covariance)
                 sum_sk += gm * fm + 2.0 * gv * s2;
@@ -653,21 +712,22 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
                 warp_mmaT<true, false, FZ_TPH>(acc, fs->Linv, rA, fs->T2, rA, Mp, ctA);
                 warp_mmaT<true, false, FZ_TPH>(acc2, fs->Linv, rB, fs->T2, rB, Mp, ctB);
             }
+            PROF_MARK(10);
             double gqa = 0.0, gqb = 0.0;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int r = (half ? rB : rA) + ar;
                 double gql = 0.0;
-                const double ur = fs->col[7][r];
+                const double ur = fs->uvec[r];
 #pragma unroll
                 for (int t = 0; t < FZ_TPH; ++t) {
                     const int c = ((half ? ctB : ctA) + t) * 8 + ac;
                     const double2 a = *reinterpret_cast<const double2*>(&fs->T1[r * FZ_LD + c]);
-                    const double g0 = fs->col[2][c], g1 = fs->col[2][c + 1];
+                    const double g0 = fs->gm[c], g1 = fs->gm[c + 1];
                     gql = fma(a.x, g0, gql);
                     gql = fma(a.y, g1, gql);
                     if (need_s) {
-                        const double w0 = fs->col[6][c], w1 = fs->col[6][c + 1];
+                        const double w0 = fs->gv2[c], w1 = fs->gv2[c + 1];
                         const double p0 = half ? acc2[t][0] : acc[t][0], p1 = half ? acc2[t][1] : acc[t][1];
                         const double2 kr = *reinterpret_cast<const double2*>(&fs->T3[r * FZ_LD + c]);
                         sum_skr = fma(fma(p0, w0, ur * g0), kr.x, sum_skr);
@@ -680,12 +740,13 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
             gqb += __shfl_xor_sync(0xffffffffu, gqb, 1); gqb += __shfl_xor_sync(0xffffffffu, gqb, 2);
             // each (row, column group) partial sum has exactly one writer
             if ((lane & 3) == 0) { fs->gq[0][rA + ar] += gqa; fs->gq[1][rB + ar] += gqb; }
+            PROF_MARK(11);
             // ---- H += (A diag(2 gv)) A^T, lower tiles ---------------------------------------------------------------
             {
                 const int ak = lane & 3;
-#pragma unroll 2
+#pragma unroll 4
                 for (int k0 = 0; k0 < 64; k0 += 4) {
-                    const double sc = fs->col[6][k0 + ak];
+                    const double sc = fs->gv2[k0 + ak];
                     const double a1 = fs->T1[(rA + ar) * FZ_LD + k0 + ak] * sc;
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
@@ -707,6 +768,7 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
                 }
             }
         }
+        if (more && tid < 64 * dd) fs->Xs[bf ^ 1][tid] = xpre;
         PROF_MARK(8);
     }
     __syncthreads();

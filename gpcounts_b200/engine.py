@@ -191,6 +191,30 @@ def fit(models: Sequence[Model], Y, scale, hyp0, chain=True, opt=None, return_th
     return stats, theta
 
 
+def predict(model: Model, theta, Xnew, Y=None, zset=0, full_cov=False, n_slots=None):
+    """Posterior mean / variance (and optionally covariance) of f at Xnew for D fitted parameter vectors theta (D, >= P)."""
+    lib = L.load()
+    dev = model.X.device
+    theta = _dev_f64(theta, dev).contiguous()
+    Xnew = _dev_f64(np.asarray(Xnew, dtype=np.float64).reshape(len(Xnew), -1), dev)
+    Y = _dev_f64(Y, dev)
+    D, T = theta.shape[0], Xnew.shape[0]
+    assert Xnew.shape[1] == model.d and theta.shape[1] >= model.P
+    arr = _models_array([model])
+    n_slots = n_slots or min(296, max(D, 1))
+    nbytes = lib.gpc_predict_workspace_bytes(arr, T, n_slots)
+    ws = _workspace(nbytes, dev)
+    mean = torch.empty(D, T, dtype=torch.float64, device=dev)
+    var = torch.empty(D, T, dtype=torch.float64, device=dev)
+    cov = torch.empty(D, T, T, dtype=torch.float64, device=dev) if full_cov else None
+    with torch.cuda.device(dev):
+        L.check(lib.gpc_predict(arr, D, Y.data_ptr() if Y is not None else None, Y.stride(0) if Y is not None else 0,
+                                theta.data_ptr(), theta.stride(0), zset, Xnew.data_ptr(), T, mean.data_ptr(), var.data_ptr(),
+                                cov.data_ptr() if cov is not None else None, ws.data_ptr(), ws.numel(), n_slots,
+                                _stream_ptr(dev)))
+    return mean, var, cov
+
+
 def dbg_linalg(op, A, B=None, nrhs=0):
     """Test hook for the CTA-level dense primitives (see include/gpcounts_b200.h)."""
     lib = L.load()

@@ -103,6 +103,10 @@ typedef struct gpc_opt {
     int32_t trace_gene;    /* record (loss, step, slope, max|g|, theta[0..3]) of every evaluation of attempt 0   */
     int32_t trace_model;   /*   of this (gene, model) ...                                                        */
     double* trace;         /*   ... into this device buffer; NULL = off                                          */
+    /* host-driven restarts (safe_mode, GPcounts_Module.py:518-525, :962-1006): device int32 [D x n_models] or NULL.  A fit
+     * whose entry is c > 0 starts at restart c (hyper-parameters of restart-table row c - 1, inducing set c), exactly as
+     * if attempts 0 .. c-1 had failed; its GPC_S_RESTARTS counts from there. */
+    const int32_t* attempt0;
 } gpc_opt_t;
 
 /* Default optimiser settings = gpflow.optimizers.Scipy / SciPy L-BFGS-B defaults with maxiter=5000. */
@@ -148,6 +152,21 @@ int gpc_fit(const gpc_model_t* models, int32_t n_models, int32_t chain, const gp
             const double* Y, const double* scale, int64_t ldy, const double* hyp0,
             double* out_stats, double* out_theta, int64_t ld_theta,
             void* workspace, size_t workspace_bytes, int32_t n_slots, void* stream);
+
+/*
+ * Batched posterior prediction of the latent function at new inputs from fitted parameter vectors.
+ * Replaces `model.predict_f(Xnew)` (and the mean / covariance behind `predict_y`, `predict_f_samples`) of the fitted gpflow
+ * models in load_predict_models (GPcounts_Module.py:930-945), infer_branching (:305-317) and the safe-mode check (:962-980).
+ *   theta     D x ld_theta  fitted parameter vectors (gpc_fit out_theta rows of this model)
+ *   Y         D x ldy       data; only read for GPC_GPR (the Gaussian posterior mean depends on y), may be NULL otherwise
+ *   Xnew      T x d         new inputs (BRANCH: [t, label])
+ *   out_mean  D x T,  out_var  D x T   mean and variance of f(Xnew);  out_cov  D x T x T full covariance or NULL
+ * Rows of genes whose Gram matrix is not positive definite are NaN.  GPC_SGPR is not supported (GPC_E_UNSUPPORTED).
+ */
+size_t gpc_predict_workspace_bytes(const gpc_model_t* model, int32_t T, int32_t n_slots);
+int gpc_predict(const gpc_model_t* model, int32_t D, const double* Y, int64_t ldy, const double* theta, int64_t ld_theta,
+                int32_t zset, const double* Xnew, int32_t T, double* out_mean, double* out_var, double* out_cov,
+                void* workspace, size_t workspace_bytes, int32_t n_slots, void* stream);
 
 /*
  * Test hooks for the CTA-level dense primitives (batched over `batch` matrices, one CTA each).

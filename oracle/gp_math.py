@@ -273,3 +273,39 @@ def initial_theta(spec, var0, ls0, alpha0, km0=35.0):
         diag = NHYP + mv + np.array([i * (i + 1) // 2 + i for i in range(mv)])
         th[diag] = 1.0
     return th
+
+
+def predict_f(theta_np, spec, Xnew, y=None, full_cov=False):
+    """gpflow ``model.predict_f(Xnew, full_cov)`` of the fitted model (reference call sites GPcounts_Module.py:930-945 via
+    predict_y / predict_f_samples, :305-317): VGP / SVGP through ``conditionals.base_conditional`` (whitened, q_sqrt),
+    GPR through the exact Gaussian conditional.  Returns (mean (T,), var (T,) | cov (T, T)) as NumPy arrays."""
+    theta = torch.as_tensor(np.asarray(theta_np, dtype=np.float64))
+    X = torch.as_tensor(spec.X)
+    Xn = torch.as_tensor(np.asarray(Xnew, dtype=np.float64).reshape(len(Xnew), -1))
+    hyp, q_mu, Lq = unpack(theta, spec)
+    var, ls, alpha, km = (softplus(hyp[i]) for i in range(NHYP))
+    T = Xn.shape[0]
+    Kss = kernel_K(spec, Xn, Xn, var, ls, square=True) if full_cov else kernel_Kdiag(spec, Xn, var)
+    if spec.kind in ("VGP", "SVGP"):
+        Zr = X if spec.kind == "VGP" else torch.as_tensor(spec.Z)
+        Kmm = kernel_K(spec, Zr, Zr, var, ls, square=True) + spec.jitter * torch.eye(Zr.shape[0])
+        Kmn = kernel_K(spec, Zr, Xn, var, ls)
+        Lm = torch.linalg.cholesky(Kmm)
+        A = torch.linalg.solve_triangular(Lm, Kmn, upper=False)
+        mean = A.T @ q_mu
+        LTA = torch.tril(Lq).T @ A
+        if full_cov:
+            cov = Kss - A.T @ A + LTA.T @ LTA
+        else:
+            cov = Kss - (A * A).sum(0) + (LTA * LTA).sum(0)
+        return mean.numpy(), cov.numpy()
+    if spec.kind == "GPR":
+        noise = GAUSS_VAR_LOWER + alpha
+        K = kernel_K(spec, X, X, var, ls, square=True) + noise * torch.eye(X.shape[0])
+        L = torch.linalg.cholesky(K)
+        A = torch.linalg.solve_triangular(L, kernel_K(spec, X, Xn, var, ls), upper=False)
+        v = torch.linalg.solve_triangular(L, torch.as_tensor(y)[:, None], upper=False)
+        mean = (A.T @ v)[:, 0]
+        cov = Kss - A.T @ A if full_cov else Kss - (A * A).sum(0)
+        return mean.numpy(), cov.numpy()
+    raise ValueError(spec.kind)

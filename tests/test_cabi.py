@@ -35,8 +35,8 @@ def test_struct_layout_matches_header(lib):
     from gpcounts_b200 import _lib
     # 10 int32 + 2 double + 4 pointers, natural alignment
     assert ctypes.sizeof(_lib.gpc_model_t) == 10 * 4 + 2 * 8 + 4 * 8
-    # 4 int32 + 2 double + 4 int32 (variant, trace_cap, trace_gene, trace_model) + 1 pointer
-    assert ctypes.sizeof(_lib.gpc_opt_t) == 4 * 4 + 2 * 8 + 4 * 4 + 8
+    # 4 int32 + 2 double + 4 int32 (variant, trace_cap, trace_gene, trace_model) + 2 pointers (trace, attempt0)
+    assert ctypes.sizeof(_lib.gpc_opt_t) == 4 * 4 + 2 * 8 + 4 * 4 + 2 * 8
 
 
 def test_defaults_and_param_count(lib):

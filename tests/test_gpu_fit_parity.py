@@ -8,14 +8,12 @@ chaotic at round-off level.  Every fixture therefore car
 start perturbed by 1e-12: fits whose two oracle runs agree are *stable* and must match tightly; the others
 are only required to land on one of the oracle's answers or between them.
 
-Even a stable fit can stop early on a plateau: SciPy's rule ends the run the first time one iteration gains less than
-2.2e-9 |f|, and along a creeping valley whether that happens at iteration 240 or 450 is decided by round-off.  Measured
-on gene 0 of the NB fixture, starts perturbed by k * 1e-13: the oracle (SciPy on the CPU) ends 3 of 32 runs 0.008 nats
-short at -424.2078 / -424.2076 / -424.2075, the GPU 2 of 32 at -424.2077 / -424.2076 (`tests/golden/
-make_perturbed_runs.py`, `tools/perturb_gene.py`) - a fit has a small *set* of outcomes, the same set on both sides.
-A dynamic-model mismatch is therefore re-examined: the GPU value must coincide with one of the oracle's 32 outcomes
-(`<fixture>_runs.npz`) or, failing that, the median of five GPU fits from perturbed starts must match the oracle; at
-most one fit per fixture may need either.
+Even a fit whose two oracle runs agree can stop early on a plateau: SciPy's rule ends the run the first time one iteration
+gains less than 2.2e-9 |f|, and along a creeping valley whether that happens at iteration 240 or 450 is decided by round-off.
+A fit therefore has a small *set* of outcomes - `<fixture>_runs.npz` holds the oracle's outcomes over 32 starts perturbed by
+k * 1e-13 (`tests/golden/make_perturbed_runs.py`, `make_large_fixtures.py`).  A GPU log-likelihood is accepted when it coincides
+with ANY of the oracle's recorded outcomes (primary run, 1e-12 run, the 32 runs); there are no retries and no substituted
+values.  That the GPU visits those outcomes with the oracle's frequencies is tested in tests/test_gpu_fit_large.py.
 """
 import os
 
@@ -45,62 +43,45 @@ def _frames(fx):
     return Xdf, Ydf, sdf
 
 
-def _median_of_perturbed_fits(fx, g, lik, sparse):
-    """Dynamic-model log-likelihood of gene g: median over five fits whose initial variance is scaled by 1 + k 1e-13."""
-    from gpcounts_b200 import Fit_GPcounts, host
-    Xdf, Ydf, sdf = _frames(fx)
-    Y1 = Ydf.iloc[[g]]
-    s1 = sdf.iloc[:, [g]] if sdf is not None else None
-    var0 = host.default_variance(Y1.values.astype(int).astype(float), lik, True)[0]
-    lls = []
-    for k in range(1, 6):
-        gp = Fit_GPcounts(Xdf, Y1, scale=s1, sparse=sparse, M=int(fx["M"]) if sparse else 0)
-        gp.initialize_hyper_parameters(variance=var0 * (1.0 + k * 1e-13))
-        lls.append(gp.Infer_trajectory(lik).values[0, 0])
-    return float(np.median(lls))
-
-
 def _oracle_outcomes(name, g):
     """Dynamic-model log-likelihoods of gene g over the oracle's 32 perturbed starts, if the fixture has them."""
     path = os.path.join(GOLD, name + "_runs.npz")
     return np.load(path)["ll_runs"][g] if os.path.exists(path) else None
 
 
-def _check_table(df, fx, K, skip=None, lik=None, sparse=False, name=None):
+def _check_table(df, fx, K, skip=None, name=None):
+    """Every per-model log-likelihood must coincide with one of the oracle's outcomes for that fit; the LLR of genes whose
+    oracle runs agree must match to 1e-4 relative (north_star), shifted by the outcome the dynamic fit landed on."""
     got = df.values.copy()
     ref, ref2 = fx["ll"], fx["ll_pert"]
     assert got.shape == ref.shape
     n_stable = 0
-    n_retried = 0
     for g in range(ref.shape[0]):
-        shift = 0.0           # oracle's alternative outcome of the dynamic fit minus its primary one (see below)
+        shift = 0.0           # oracle outcome the dynamic fit coincides with, minus the oracle's primary outcome
         for k in range(K):
             a, b = ref[g, k], ref2[g, k]
             stable = abs(a - b) <= 1e-6 * abs(a)
             n_stable += int(stable)
             if skip is not None and (g, k) in skip:
                 continue
-            # unstable fits (the oracle's own two runs disagree): plateau stops, chaotic at round-off level - 3e-4 relative
+            outcomes = [a, b]
+            if k == 0 and name is not None:
+                runs = _oracle_outcomes(name, g)
+                if runs is not None:
+                    outcomes += list(runs)
+            outcomes = np.array(outcomes)
+            # unstable fits (the oracle's two runs disagree): plateau stops, chaotic at round-off level - the envelope
             tol = LL_RTOL * abs(a) if stable else max(10.0 * abs(a - b), 3e-4 * abs(a))
-            if abs(got[g, k] - a) > tol and k == 0 and K == 2 and lik is not None and got[g, k] < a:
-                # an early plateau stop of the dynamic fit (lower ELBO, see the module docstring)
-                n_retried += 1
-                runs = _oracle_outcomes(name, g) if name else None
-                if runs is not None and np.abs(runs - got[g, k]).min() <= tol:
-                    shift = runs[np.abs(runs - got[g, k]).argmin()] - a     # one of the oracle's own outcomes
-                    continue
-                med = _median_of_perturbed_fits(fx, g, lik, sparse)
-                assert abs(med - a) <= tol, (g, k, got[g, k], med, a, b)
-                got[g, K] += med - got[g, k]
-                got[g, k] = med
-            assert abs(got[g, k] - a) <= tol, (g, k, got[g, k], a, b)
+            j = int(np.abs(outcomes - got[g, k]).argmin())
+            assert abs(got[g, k] - outcomes[j]) <= tol, (g, k, got[g, k], a, b)
+            if k == 0:
+                shift = outcomes[j] - a
         a, b = ref[g, K], ref2[g, K]
         if skip is not None and any(gg == g for gg, _ in skip):
             continue
         if abs(a - b) <= 1e-5 * abs(a) + 1e-5:
             assert abs(got[g, K] - (a + shift)) <= LLR_RTOL * abs(a) + LLR_ATOL, (g, got[g, K], a, shift)
     assert n_stable >= 0.7 * ref.shape[0] * K
-    assert n_retried <= 1
 
 
 @pytest.mark.parametrize("name", ["one_sample_sparse_nb", "one_sample_sparse_poisson", "one_sample_sparse_zinb"])
@@ -112,7 +93,7 @@ def test_one_sample_sparse(name):
     df = gp.One_sample_test(str(fx["lik"]))
     assert list(df.columns) == ["Dynamic_model_log_likelihood", "Constant_model_log_likelihood", "log_likelihood_ratio"]
     assert list(df.index) == list(Ydf.index)
-    _check_table(df, fx, 2, lik=str(fx["lik"]), sparse=True, name=name)
+    _check_table(df, fx, 2, name=name)
     assert (gp.fit_stats["status"] == 0).all()
     out = gp.calculate_FDR(df)
     assert {"p_value", "q_value"} <= set(out.columns)
@@ -139,15 +120,9 @@ def test_infer_trajectory_matches_dynamic_column():
     assert list(df.columns) == ["Dynamic_model_log_likelihood"]
     ref = fx["ll"][:, 0]
     stable = np.abs(ref - fx["ll_pert"][:, 0]) <= 1e-6 * np.abs(ref)
-    bad = stable & ~(np.abs(df.values[:, 0] - ref) <= LL_RTOL * np.abs(ref))
-    assert bad.sum() <= 1                      # at most one early plateau stop, re-examined as in _check_table
-    for g in np.nonzero(bad)[0]:
-        assert df.values[g, 0] < ref[g]
-        runs = _oracle_outcomes("one_sample_sparse_nb", g)
-        if runs is not None and np.abs(runs - df.values[g, 0]).min() <= LL_RTOL * abs(ref[g]):
-            continue
-        med = _median_of_perturbed_fits(fx, g, "Negative_binomial", True)
-        assert abs(med - ref[g]) <= LL_RTOL * abs(ref[g]), (g, df.values[g, 0], med, ref[g])
+    for g in np.nonzero(stable)[0]:
+        outcomes = np.r_[ref[g], _oracle_outcomes("one_sample_sparse_nb", g)]
+        assert np.abs(outcomes - df.values[g, 0]).min() <= LL_RTOL * abs(ref[g]), (g, df.values[g, 0], ref[g])
 
 
 def test_two_samples():
@@ -251,14 +226,17 @@ def test_c5_headline_sample():
     assert well.sum() >= 8, well.sum()
     assert np.all(np.abs(got[well, 0] - ref[well, 0]) <= LL_RTOL * np.abs(ref[well, 0])), (got[well, 0], ref[well, 0])
     assert np.all(np.abs(got[well, 2] - ref[well, 2]) <= LLR_RTOL * np.abs(ref[well, 2]) + LLR_ATOL)
-    # (2) all genes: inside the envelope of the oracle's own run-to-run variability.  One gene in 48 may end in a
-    # different basin: a quasi-Newton trial step occasionally lands where the ELBO is -inf with a NaN gradient, after
-    # which SciPy's L-BFGS-B (and therefore this optimiser) retreats to the current iterate and reports convergence;
-    # whether that happens is decided by 1e-14-level differences of the start point.
+    # (2) all genes: the dynamic fit ends inside the set of outcomes the oracle itself produces for that gene over 32 starts
+    # perturbed by k * 1e-13 (c5_sample_sparse_nb_runs.npz; for 18 of the 48 genes that set is a continuum up to 2 nats
+    # wide - constant genes whose RBF fit creeps along a flat valley), and so does the LLR
+    runs = np.c_[_load("c5_sample_sparse_nb_runs")["ll_runs"], ref[:, 0], ref2[:, 0]]
+    tol0 = 1e-4 * np.abs(ref[:, 0])
+    lo, hi = runs.min(axis=1) - tol0, runs.max(axis=1) + tol0
+    assert np.all((got[:, 0] >= lo) & (got[:, 0] <= hi)), np.c_[got[:, 0], lo, hi][(got[:, 0] < lo) | (got[:, 0] > hi)]
+    cst_err = np.abs(got[:, 1] - ref[:, 1])
+    assert np.all((got[:, 2] >= lo - ref[:, 1] - cst_err - 1e-9) & (got[:, 2] <= hi - ref[:, 1] + cst_err + 1e-9))
     spread = np.abs(ref[:, 2] - ref2[:, 2])
     err = np.abs(got[:, 2] - ref[:, 2])
-    envelope = max(1.5 * spread.max(), 0.5)
-    assert (err > envelope).sum() <= 1, (np.sort(err)[-3:], spread.max())
     assert np.median(err) <= max(3 * np.median(spread), 2e-3), (np.median(err), np.median(spread))
     # (3) differential-expression calls: >= 99 % is the north_star figure for whole-genome runs; on 48 genes a single
     # basin flip is already 2 %, so at most one disagreeing call is allowed here

@@ -112,8 +112,9 @@ def test_api_surface_matches_reference():
     df = pd.DataFrame({"log_likelihood_ratio": [0.253854, 22.315595]})
     out = gp.calculate_FDR(df)
     assert abs(out["p_value"][1] - 2.378719e-11) < 1e-16
-    with pytest.raises(NotImplementedError):
-        Fit_GPcounts(X, Y, safe_mode=True)
+    assert Fit_GPcounts(X, Y, safe_mode=True).safe_mode is True
+    for name in ["load_predict_models", "get_file_name", "Model_selection_test"]:
+        assert callable(getattr(Fit_GPcounts, name)), name
 
 
 def test_per_gene_inducing_selection_matches_host_recurrence():

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 PROF = os.path.join(ROOT, "gpcounts_b200", "lib", "libgpcounts_b200_prof.so")
 if len(sys.argv) > 1 and sys.argv[1] == "build":
-    src = [os.path.join(ROOT, "gpcounts_b200", "csrc", f) for f in ("gpc_api.cu", "gpc_dense.cu", "gpc_fused.cu")]
+    src = [os.path.join(ROOT, "gpcounts_b200", "csrc", f) for f in ("gpc_api.cu", "gpc_dense.cu", "gpc_fused.cu", "gpc_small.cu")]
     flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-DGPC_PHASE_PROF"]
     objs = []
     procs = []
@@ -35,14 +35,14 @@ lib = _lib.load()
 lib.gpc_dbg_phase_prof.argtypes = [C.c_int, C.c_void_p]
 out = (C.c_ulonglong * 16)()
 names = ["setup(Z,Lq,Kuu,W)", "cholesky", "tri-inverse", "Lm save,u,lgamma pre-pass", "tile load + Kuf exp", "A = Linv Kuf", "C = W A",
-         "stats + quadrature", "S product + gq + rank update", "end phase"]
+         "stats + quadrature", "rank update H += A D A^T", "end phase", "S product Linv^T C", "S epilogue + gq"]
 for variant in (-1, 0):
     st, _ = engine.fit(models, Y, None, h, chain=True, opt=engine.default_opt(variant=variant), return_theta=False)
     torch.cuda.synchronize()
     assert lib.gpc_dbg_phase_prof(2 if variant < 0 else 0, out) == 0
     print('instantiation', 'f256' if variant < 0 else 't256')
     n = out[15]
-    tot = sum(out[i] for i in range(10))
+    tot = sum(out[i] for i in range(12))
     print("evaluations %d, cycles per evaluation %.0f (%.1f us at 1965 MHz)" % (n, tot / n, tot / n / 1965))
     for i, nm in enumerate(names):
         print("  %-32s %8.0f cycles  %5.1f %%" % (nm, out[i] / n, 100.0 * out[i] / tot))
