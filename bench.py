@@ -414,6 +414,7 @@ def main():
     ap.add_argument("--cpu-genes", type=int, default=0, help="genes in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--maxiter", type=int, default=5000, help="profiling only: cap L-BFGS iterations")
+    ap.add_argument("--variant", type=int, default=-1, help="A/B measurements only: force a kernel instantiation (gpc_opt_t.variant)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -440,7 +441,7 @@ def main():
     else:
         wl = Workload(args.workload, args.genes, 1234 + 1000 * rank)
         G = wl.G
-    opt = engine.default_opt(maxiter=args.maxiter)
+    opt = engine.default_opt(maxiter=args.maxiter, variant=args.variant)
     wl.prepare_device(dev, nsteps, opt)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize(dev)

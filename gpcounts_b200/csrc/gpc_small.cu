@@ -3,5 +3,5 @@
 #define GPC_VARIANT s64
 #define GPC_THREADS 64
 #define GPC_SMALL_ONLY
-#define GPC_MIN_BLOCKS 8
+#define GPC_MIN_BLOCKS 6      // shared memory allows six 37 KB CTAs per SM at N = 18: 170 registers per thread
 #include "kernels.cuh"

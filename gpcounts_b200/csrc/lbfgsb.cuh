@@ -294,130 +294,6 @@ __device__ void subsm_solve(OptSmem* os, int col) {
     __syncwarp();
 }
 
-// ---- register versions of formk / subsm / formt ------------------------------------------------------------------------
-// The 2m x 2m middle matrix lives in the registers of ONE warp, lane j holding column j of the upper-triangular factor
-// (c[i] = U[i][j], i <= j); pivots and row entries travel by shuffle, square roots / divisions are branch-free
-// (gpc_rsqrt, gpc_rcp).  Blocks sit at fixed offsets (block 1 = rows / columns 0..9, block 2 = 10..19) and unused rows are
-// identity, so every register index is a compile-time constant whatever `col` is.  The arithmetic is the right-looking
-// elimination of warp_chol_upper / formk_free above (same order of the updates); ~2 us instead of ~25 us per iteration.
-
-// In-place upper Cholesky (LEL^T form when SPLIT: block-2 rows accumulate + instead of - while k runs over block 1).
-// Returns 0 or the 1-based index of the first non-positive pivot (warp-uniform).
-template <int NN, bool SPLIT>
-__device__ __forceinline__ int warp_chol_cols(double (&c)[NN]) {
-    const unsigned FULL = 0xffffffffu;
-    int info = 0;
-#pragma unroll
-    for (int k = 0; k < NN; ++k) {
-        const double piv = __shfl_sync(FULL, c[k], k);
-        if (!(piv > 0.0) && info == 0) info = k + 1;
-        const double rinv = gpc_rsqrt(piv);
-        double sq = piv * rinv;
-        sq = fma(fma(-sq, sq, piv), 0.5 * rinv, sq);
-        const int lane = threadIdx.x & 31;
-        const double ukj = (lane == k) ? sq : c[k] * rinv;          // my entry of row k (valid for lane >= k)
-        c[k] = ukj;
-#pragma unroll
-        for (int i = k + 1; i < NN; ++i) {
-            const double uki = __shfl_sync(FULL, ukj, i);
-            if (SPLIT && k < NN / 2 && i >= NN / 2) c[i] = fma(uki, ukj, c[i]);
-            else c[i] = fma(-uki, ukj, c[i]);
-        }
-    }
-    return info;
-}
-
-// formk (all variables free) + subsm on one warp.  `updated`: the memory changed since the last call (else the factor kept
-// in os->WN is reused).  On success os->wv holds K^-1 wv in the layout the direction pass expects.  Returns 0 / -1 / -2.
-__device__ __forceinline__ int formk_subsm_reg(OptSmem* os, int col, double theta, bool updated) {
-    const unsigned FULL = 0xffffffffu;
-    constexpr int H = GPC_MMAX, NN = 2 * GPC_MMAX;
-    const int lane = threadIdx.x & 31;
-    double* WN = &os->WN[0][0];
-    double c[NN];
-    int info = 0;
-    if (updated) {
-        // column `lane` of [Y'Y / theta + D, R_z'; . , 0] (upper part), identity on unused rows / columns
-        const int jb = lane < H ? lane : lane - H;                  // index within the block
-        const bool jact = lane < NN && jb < col;
-#pragma unroll
-        for (int i = 0; i < NN; ++i) {
-            const int ib = i < H ? i : i - H;
-            double v = (i == lane) ? 1.0 : 0.0;                     // identity on unused rows / columns
-            if (jact && ib < col) {
-                if (i < H && lane < H) v = (i <= lane) ? os->YY[lane][i] / theta + (i == lane ? os->SY[i][i] : 0.0) : 0.0;
-                else if (i < H) v = (ib >= jb) ? os->RZ[jb][ib] : 0.0;     // block (1,2) = R_z': [i][j] = s_j . y_i, j <= i
-                else v = 0.0;                                        // block (2,2) starts at zero, diagonal included
-            }
-            c[i] = v;
-        }
-        // an active block-2 column starts from zero on its diagonal (theta S'AA'S = 0): the + updates of block 1 fill it
-        info = warp_chol_cols<NN, true>(c);
-        if (info != 0) return info <= H ? -1 : -2;
-        if (lane < NN) {
-#pragma unroll
-            for (int i = 0; i < NN; ++i) WN[i * NN + lane] = c[i];
-        }
-        __syncwarp();
-    } else {
-#pragma unroll
-        for (int i = 0; i < NN; ++i) c[i] = (lane < NN) ? WN[i * NN + lane] : ((i == lane) ? 1.0 : 0.0);
-    }
-    // wv = [Y'r ; theta S'r] with r = -g, blocks at fixed offsets
-    double b = 0.0;
-    if (lane < col) b = -os->dots[lane][5];
-    else if (lane >= H && lane - H < col) b = -theta * os->dots[lane - H][4];
-    // own diagonal reciprocal
-    double dg = 1.0;
-#pragma unroll
-    for (int i = 0; i < NN; ++i) if (i == lane) dg = c[i];
-    const double dinv = gpc_rcp(dg);
-    // U^T x = b  (forward; lane i owns column i of U = row i of U^T)
-#pragma unroll
-    for (int k = 0; k < NN; ++k) {
-        const double xk = __shfl_sync(FULL, b * dinv, k);
-        b = (lane == k) ? xk : ((lane > k) ? fma(-c[k], xk, b) : b);
-    }
-    if (lane < H) b = -b;
-    // U x = b  (backward; needs rows: lane i reads row i of the factor from shared memory)
-    double u[NN];
-#pragma unroll
-    for (int j = 0; j < NN; ++j) u[j] = (lane < NN) ? WN[lane * NN + j] : 0.0;
-#pragma unroll
-    for (int k = NN - 1; k >= 0; --k) {
-        const double xk = __shfl_sync(FULL, b * dinv, k);
-        b = (lane == k) ? xk : ((lane < k) ? fma(-u[k], xk, b) : b);
-    }
-    if (lane < col) os->wv[lane] = b;
-    else if (lane >= H && lane - H < col) os->wv[col + lane - H] = b;
-    return 0;
-}
-
-// formt: T = theta SS + L D^-1 L^T positive definite?  0 on success (one warp, registers).
-__device__ __forceinline__ int formt_check_reg(OptSmem* os, int col, double theta) {
-    const unsigned FULL = 0xffffffffu;
-    constexpr int H = GPC_MMAX;
-    const int lane = threadIdx.x & 31;
-    const double dmine = (lane < col) ? gpc_rcp(os->SY[lane][lane]) : 0.0;
-    double dk[H];
-#pragma unroll
-    for (int k = 0; k < H; ++k) dk[k] = __shfl_sync(FULL, dmine, k);       // 1 / SY[k][k]
-    double c[H];
-#pragma unroll
-    for (int i = 0; i < H; ++i) {
-        double v = (i == lane) ? 1.0 : 0.0;
-        if (lane < col && i <= lane) {
-            double ddum = 0.0;
-#pragma unroll
-            for (int k = 0; k < H; ++k)
-                if (k < i) ddum = fma(os->SY[i][k] * os->SY[lane][k], dk[k], ddum);
-            v = ddum + theta * os->SS[i][lane];
-        }
-        c[i] = v;
-    }
-    return warp_chol_cols<H, false>(c);
-}
-
 struct OptResult {
     int task;          // TASK_*
     int nit, nfev;
@@ -767,12 +643,25 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
         __syncthreads();
         // formt (acceptance of the new pair) on warp 0 and, concurrently on warp 1, the direction solve of the next
         // iteration: formk (only when a pair was stored) and subsm with the dot products of the new gradient
+        // (A register-resident variant of these three - lane per column, pivots by shuffle, fully unrolled 20-step
+        // elimination - was measured in round 2: 13 k SASS instructions that gained 1 % on the 256-thread kernel and cost the
+        // 64-thread small-N kernel most of its time in instruction-cache misses (stall_no_inst 44-69 %).  The compact
+        // shared-memory loops below are what ships.)
         if (!skip && warp == 0) {
-            const int info = formt_check_reg(os, col, theta);
+            const int info = formt_check(os, col, theta);
             if (lane == 0) os->info = info;
         }
         if (warp == 1 && col > 0) {
-            const int info = formk_subsm_reg(os, col, theta, updated);
+            int info = 0;
+            if (updated) info = formk_free(os, col, theta);
+            if (info == 0) {
+                if (lane < col) {
+                    os->wv[lane] = -os->dots[lane][5];                 // Y_j . r, r = -g
+                    os->wv[col + lane] = -theta * os->dots[lane][4];   // theta * S_j . r
+                }
+                __syncwarp();
+                subsm_solve(os, col);
+            }
             if (lane == 0) os->info_dir = info;
         }
         __syncthreads();

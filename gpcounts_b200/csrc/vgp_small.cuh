@@ -27,6 +27,8 @@ struct SmallHdr {
     double red[80];
     double fmean[GPC_SMALL_NMAX], fvar[GPC_SMALL_NMAX], gm[GPC_SMALL_NMAX], gv[GPC_SMALL_NMAX], qmu[GPC_SMALL_NMAX];
     double dinv[GPC_SMALL_NMAX];                 // 1 / L_ii
+    double yv[GPC_SMALL_NMAX], sv[GPC_SMALL_NMAX];   // counts and scale factors of the gene
+    double Xs[2 * GPC_SMALL_NMAX];               // inputs (d <= 2)
     int ok;
 };
 
@@ -70,8 +72,9 @@ __device__ __forceinline__ SmallPart small_nodes_nb(const LikParams& lp, double 
     return o;
 }
 
+// (out of line: the NB path is the hot one, and this kernel lives or dies by its instruction-cache footprint)
 template <int ISTEP>
-__device__ __forceinline__ SmallPart small_nodes_zinb(const LikParams& lp, double fm, double sd, double y, int i0) {
+__device__ __noinline__ SmallPart small_nodes_zinb(const LikParams& lp, double fm, double sd, double y, int i0) {
     SmallPart o{0.0, 0.0, 0.0, 0.0, 0.0, false};
     const double alpha = lp.alpha, k = lp.k, ia = k, ia2 = k * k, km = lp.km;
     for (int i = i0; i < GPC_NGH; i += ISTEP) {
@@ -135,7 +138,28 @@ __device__ __noinline__ int eval_vgp_small(const ModelDev& md, const double* y, 
     }
     const double* q_mu = theta + GPC_NHYP;
     const double* lq_packed = theta + GPC_NHYP + N;
-    for (int i = tid; i < N; i += GPC_THREADS) hd->qmu[i] = q_mu[i];
+    // everything the evaluation reads from global memory is staged once, with independent loads (every later access is
+    // shared memory: at this size a dependent L2 round trip costs as much as a whole phase of the evaluation)
+    for (int i = tid; i < N; i += GPC_THREADS) {
+        hd->qmu[i] = q_mu[i];
+        hd->yv[i] = y[i];
+        hd->sv[i] = scale ? scale[i] : 1.0;
+    }
+    for (int i = tid; i < N * md.d; i += GPC_THREADS) hd->Xs[i] = md.X[i];
+    for (int e0 = tid; e0 < N * N; e0 += 4 * GPC_THREADS) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * GPC_THREADS;
+            const int i = e < N * N ? small_div(e, ninv) : 0, j = e - i * N;
+            v[u] = (e < N * N && j <= i) ? lq_packed[tri_index(i, j)] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * GPC_THREADS;
+            if (e < N * N) { const int i = small_div(e, ninv), j = e - i * N; Lq[i * ld + j] = v[u]; }
+        }
+    }
     __syncthreads();
     const KernParams& kp = hd->kp;
     const LikParams& lp = hd->lp;
@@ -145,19 +169,17 @@ __device__ __noinline__ int eval_vgp_small(const ModelDev& md, const double* y, 
     // ---- Gram (lower part; the factorisation reads only it) and q_sqrt ------------------------------------------------
     for (int e = tid; e < N * N; e += GPC_THREADS) {
         const int i = small_div(e, ninv), j = e - i * N;
-        double kv = 0.0, lq = 0.0;
+        double kv = 0.0;
         if (j <= i) {
-            lq = lq_packed[tri_index(i, j)];
             if (md.kernel == GPC_CONST) kv = kp.var;
             else {
                 bool cross;
-                const double r2 = kern_r2(kp, md.X + (size_t)i * dd, md.X + (size_t)j * dd, cross);
+                const double r2 = kern_r2(kp, hd->Xs + i * dd, hd->Xs + j * dd, cross);
                 kv = small_kval(kp, r2, cross);
             }
             if (i == j) kv += shift;
         }
         Lm[i * ld + j] = kv;
-        Lq[i * ld + j] = lq;
     }
     __syncthreads();
     // ---- L = chol(K): left-looking, thread i owns row i; every thread recomputes the pivot from row j (one barrier per
@@ -229,8 +251,8 @@ __device__ __noinline__ int eval_vgp_small(const ModelDev& md, const double* y, 
             }
             // ---- quadrature of point n on its GPC_SMALL_LPP lanes --------------------------------------------------------
             const double fm = s1, fv = s2;
-            const double yy = v ? y[n] : 0.0;
-            const double sc = (v && scale) ? scale[n] : 1.0;
+            const double yy = v ? hd->yv[n] : 0.0;
+            const double sc = v ? hd->sv[n] : 1.0;
             double ve = 0.0, gm = 0.0, gz = 0.0, da = 0.0, dk = 0.0;
             bool poison = false;
             if (md.lik == GPC_POISSON) {
@@ -343,7 +365,7 @@ __device__ __noinline__ int eval_vgp_small(const ModelDev& md, const double* y, 
             if (md.kernel == GPC_CONST) a2[0] += s;
             else {
                 bool cross;
-                const double r2 = kern_r2(kp, md.X + (size_t)i * dd, md.X + (size_t)j * dd, cross);
+                const double r2 = kern_r2(kp, hd->Xs + i * dd, hd->Xs + j * dd, cross);
                 const double k0 = small_kval(kp, r2, cross);
                 kern_grad_acc(kp, s, k0, r2, cross, a2[0], a2[1]);
             }

@@ -103,6 +103,11 @@ def default_opt(**over):
     return o
 
 
+def _ld(t):
+    """Leading dimension of a 2-D/3-D device tensor; size-1 leading dims can carry arbitrary strides in torch."""
+    return int(t.stride(0)) if t.shape[0] > 1 else int(np.prod(t.shape[1:]))
+
+
 def _stream_ptr(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -152,7 +157,7 @@ def elbo_grad(model: Model, Y, scale, theta, zset=0, n_slots=None):
     grad = torch.empty(D, model.P, dtype=torch.float64, device=dev)
     status = torch.empty(D, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        L.check(lib.gpc_elbo_grad(arr, D, Y.data_ptr(), scale.data_ptr() if scale is not None else None, Y.stride(0),
+        L.check(lib.gpc_elbo_grad(arr, D, Y.data_ptr(), scale.data_ptr() if scale is not None else None, _ld(Y),
                                   theta.data_ptr(), zset, elbo.data_ptr(), grad.data_ptr(), status.data_ptr(),
                                   ws.data_ptr(), ws.numel(), n_slots, _stream_ptr(dev)))
     return elbo, grad, status
@@ -185,7 +190,7 @@ def fit(models: Sequence[Model], Y, scale, hyp0, chain=True, opt=None, return_th
     theta = torch.empty(D, K, Pmax, dtype=torch.float64, device=dev) if return_theta else None
     with torch.cuda.device(dev):
         L.check(lib.gpc_fit(arr, K, int(chain), C.byref(opt), D, Y.data_ptr(),
-                            scale.data_ptr() if scale is not None else None, Y.stride(0), hyp0.data_ptr(),
+                            scale.data_ptr() if scale is not None else None, _ld(Y), hyp0.data_ptr(),
                             stats.data_ptr(), theta.data_ptr() if theta is not None else None, Pmax,
                             ws.data_ptr(), ws.numel(), n_slots, _stream_ptr(dev)))
     return stats, theta
@@ -208,8 +213,8 @@ def predict(model: Model, theta, Xnew, Y=None, zset=0, full_cov=False, n_slots=N
     var = torch.empty(D, T, dtype=torch.float64, device=dev)
     cov = torch.empty(D, T, T, dtype=torch.float64, device=dev) if full_cov else None
     with torch.cuda.device(dev):
-        L.check(lib.gpc_predict(arr, D, Y.data_ptr() if Y is not None else None, Y.stride(0) if Y is not None else 0,
-                                theta.data_ptr(), theta.stride(0), zset, Xnew.data_ptr(), T, mean.data_ptr(), var.data_ptr(),
+        L.check(lib.gpc_predict(arr, D, Y.data_ptr() if Y is not None else None, _ld(Y) if Y is not None else 0,
+                                theta.data_ptr(), _ld(theta), zset, Xnew.data_ptr(), T, mean.data_ptr(), var.data_ptr(),
                                 cov.data_ptr() if cov is not None else None, ws.data_ptr(), ws.numel(), n_slots,
                                 _stream_ptr(dev)))
     return mean, var, cov

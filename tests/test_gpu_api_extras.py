@@ -90,3 +90,34 @@ def test_safe_mode_restarts_only_the_fits_that_fail_the_predictive_check():
     assert np.array_equal(df.values[same, 0], ref.values[same, 0])
     assert np.isfinite(df.values[:, 0]).all()
     assert (st.restarts <= 10).all()
+
+
+def test_model_selection_table():
+    """Reference :163-229 (see the method's docstring for what the reference's kernel switch effectively fits)."""
+    from gpcounts_b200 import Fit_GPcounts
+    X, Y, Xdf, Ydf = _frames(3, 40, 13)
+    gp = Fit_GPcounts(Xdf, Ydf)
+    out = gp.Model_selection_test("Negative_binomial")
+    assert {"Gene", "Model", "BIC", "p_value", "q_value", "Dynamic_model_log_likelihood", "Constant_model_log_likelihood",
+            "log_likelihood_ratio", "Linear_probability", "Periodic_probability", "RBF_probability"} <= set(out.columns)
+    ref = Fit_GPcounts(Xdf, Ydf).One_sample_test("Negative_binomial")
+    rbf = out[out.Model == "RBF"].set_index("Gene").loc[list(ref.index)]
+    assert np.array_equal(rbf["log_likelihood_ratio"].values, ref["log_likelihood_ratio"].values)
+    assert np.allclose(rbf["BIC"].values, -2 * ref["Dynamic_model_log_likelihood"].values + 4 * np.log(40))
+    assert np.allclose(out[["Linear_probability", "Periodic_probability", "RBF_probability"]].sum(axis=1), 1.0)
+
+
+def test_sharded_fit_equals_single_gpu_bit_for_bit():
+    """SURVEY 8e: genes r::G per rank, no collective on the fit path, one all_gather of the statistics - the table of a
+    2-GPU run (torchrun, NCCL) equals the single-GPU table bit for bit.  Needs two visible GPUs."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "check_sharded.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "sharded == single: True" in out.stdout, out.stdout[-2000:]

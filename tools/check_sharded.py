@@ -16,5 +16,5 @@ dist.barrier()
 dist.destroy_process_group()
 ref = Fit_GPcounts(Xdf, Ydf, sparse=True, M=16).One_sample_test("Negative_binomial")     # unsharded on this GPU
 same = np.array_equal(df.values, ref.values, equal_nan=True)
-print("rank %d/%d sharded == single-GPU bit-for-bit: %s (%d genes)" % (rank, world, same, len(df)))
+print("rank %d/%d sharded == single: %s (%d genes, bit for bit)" % (rank, world, same, len(df)))
 sys.exit(0 if same else 1)
