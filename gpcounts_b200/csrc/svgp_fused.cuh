@@ -49,15 +49,17 @@ struct FzCfg {
 };
 
 struct FusedSmem {
-    double T0[FZ_MAT];              // Kuf tile            (end phase: Lq)
-    double T1[FZ_MAT];              // A tile              (setup: Lq; end phase: H / Lm-bar / T)
-    double T2[FZ_MAT];              // C = W A             (end phase: GLq / Lm)
-    double T3[FZ_MAT];              // Kuf o R^2           (end phase: G / P / Kbar)
+    double T0[FZ_MAT];              // A tile              (setup: scratch of the inverse; end phase: Lq)
+    double T1[FZ_MAT];              // tile loop: per-thread stash of the H accumulators and running sums (setup: Lq; end phase: H / Lm-bar / T)
+    double T2[FZ_MAT];              // C = W A             (setup: Kuu -> Lm; end phase: GLq / Lm)
+    double T3[FZ_MAT];              // Kuf o R^2           (end phase: gq partial sums / G / P / Kbar)
     double Linv[FZ_MAT];            // Lm^-1 (lower)
     double W[FZ_MAT];               // Lq Lq^T - I (symmetric)
     double qmu[64];
-    double gq[2 * FZ_WPR][64];      // A g_m accumulators, one per column group of a tile (deterministic sums)
+    double gq[64];                  // A g_m summed over all tiles (formed in the end phase from the per-warp sums)
+    double gqw[FZ_NW][64];          // A g_m over the columns of one warp (one writer per entry: deterministic sums)
     double gm[64], gv2[64];         // per column of the current tile: d VE / d fmean, 2 d VE / d fvar
+    int rk[FZ_NW][8];               // rank-update tiles of each warp: row offsets of a1 / a2, five slots, k-range of slot 4
     double uvec[64];                // u = Lm^-T q_mu (per row)
     alignas(128) double ytile[2][64];   // counts of the current / next column tile   (TMA destinations, double-buffered)
     alignas(128) double stile[2][64];   // scale factors likewise
@@ -66,7 +68,6 @@ struct FusedSmem {
     double red2[80];                // reduction scratch for up to 10 sums (cta_sum_n<K> uses K x 8 doubles)
     int chol_ok;                    // blocked Cholesky: all pivots positive so far
     double Zs[64 * 2];              // inducing inputs (d <= 2)
-    double Xs[2][64 * 2];           // inputs of the current / next column tile
     FzCfg cfg;
     KernParams kp;                  // per-evaluation constants live here rather than in registers: the evaluator
     LikParams lp;                   // is register-bound (rank-update accumulators), reloads from smem are cheap
@@ -345,6 +346,7 @@ __device__ __forceinline__ LikPart lik_nodes_nb(const LikParams& lp, double fm, 
 // The body is force-inlined into its two users: the eval-only kernel (directly) and the out-of-line wrapper
 // eval_svgp_fused() that the fit kernel calls - ptxas register-allocates an out-of-line clone per kernel, and
 // the clone under the small eval-only kernel otherwise ends up with ~1.5 KB of spills.
+template <int NRB>
 __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const double* Z, const double* y,
                                                     const double* scale, const double* theta, double* grad,
                                                     double* f_out, const SlotWs& ws, FusedSmem* fs) {
@@ -354,7 +356,7 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
     fs = reinterpret_cast<FusedSmem*>(g_smem);
     PROF_DECL;
     const int N = md.N, M = md.M, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nrb = (M + 7) >> 3, Mp = nrb * 8;          // 8-row blocks in use
+    const int nrb = NRB ? NRB : ((M + 7) >> 3), Mp = nrb * 8;   // 8-row blocks in use (NRB = 8: compile-time for M > 56)
     if (tid == 0) {
         const Hyper h0 = hyper_from_theta(md, theta);
         kern_setup(fs->kp, md, h0.var, h0.ls);
@@ -375,11 +377,8 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
 
     // ---- setup: Z, q_mu, Lq -> W = Lq Lq^T - I, Kuu -> Lm -> Linv, u = Linv^T q_mu --------------------------------
     for (int i = tid; i < 64 * 2; i += GPC_THREADS) fs->Zs[i] = (i < M * dd) ? Z[i] : 0.0;
-    if (tid < 64) {
-        fs->qmu[tid] = tid < M ? q_mu[tid] : 0.0;
-#pragma unroll
-        for (int q = 0; q < 2 * FZ_WPR; ++q) fs->gq[q][tid] = 0.0;
-    }
+    if (tid < 64) fs->qmu[tid] = tid < M ? q_mu[tid] : 0.0;
+    for (int i = tid; i < FZ_NW * 64; i += GPC_THREADS) (&fs->gqw[0][0])[i] = 0.0;
     __syncthreads();
 #pragma unroll 4
     for (int idx = tid; idx < 64 * 64; idx += GPC_THREADS) {
@@ -524,30 +523,64 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
     }
 
     // ---- column tiles -------------------------------------------------------------------------------------------
-    // M x 64 products: warp p owns row block p for column tiles 0..3 and row block nrb-1-p for column tiles 4..7,
-    // which balances the triangular k-ranges (cost rb+1 resp. nrb-rb).  The rank update H += (A D) A^T (lower tiles
-    // only) is balanced the same way: the two warps of a pair (p, nrb-1-p) split the nrb+1 tiles of their two row
-    // blocks - segment A = own row block (the low warp takes all its tiles, the high warp the tiles the low one
-    // leaves), segment B = the first tiles of the partner's row block (low warp only).
-    const int pr = warp;
-    const bool active = pr < nrb;
-    const int rA = pr * 8, rB = (nrb - 1 - pr) * 8;
-    const int ctA = 0, ctB = 4;
-    const int partner = nrb - 1 - pr, share = (nrb + 2) >> 1;          // ceil((nrb + 1) / 2) tiles per warp
-    int hA0 = 0, hA1 = 0, hB1 = 0;                                      // segment A: tiles [hA0, hA1); segment B: [0, hB1)
-    if (active) {
-        if (pr < partner) { hA0 = 0; hA1 = pr + 1; hB1 = max(0, share - (pr + 1)); }
-        else if (pr == partner) { hA0 = 0; hA1 = pr + 1; }
-        else { hA0 = max(0, share - (partner + 1)); hA1 = pr + 1; }
+    // Column-owner decomposition: warp w owns the 8 data columns [8w, 8w+8) of every 64-column tile and carries them
+    // through the whole chain on its own - Gram entries -> A = Linv Kuf -> C = W A -> (fmean, fvar) -> quadrature ->
+    // S = Linv^T C -> <S o Kuf, R^2>, gq partial sums - with warp-level synchronisation only: a column of A, C or S depends
+    // on the same column of its operand, never on a neighbour's.  The Gram entries are produced directly in the DMMA
+    // B-fragment layout (lane (ar, ak) holds rows 4j + ak of column 8w + ar) and never touch shared memory; A, C and
+    // Kuf o R^2 go through the warp's own 64 x 8 slab of T0, T2, T3 (accumulator layout -> B-fragment layout).
+    // Only the rank update H += (A D) A^T contracts over the columns of all warps: one CTA barrier before it (the tile's A
+    // and 2 g_v are complete) and one after the next tile's Gram entries (every warp has left the rank update, T0 may be
+    // overwritten).  The evaluator is register-bound, so the state that has to survive a whole tile - the H accumulators and
+    // the six running sums - is parked in shared memory (the T1 matrix is idle during the loop) instead of being spilled
+    // to local memory behind the tiny L1 that the shared-memory carve-out leaves.
+    const int ar = lane >> 2, ak = lane & 3, ac = 2 * ak;
+    const int cw = warp * 8, cg = cw + ar;            // slab origin; the column this lane builds Gram entries / nodes for
+    const bool active = warp < nrb;
+    // Rank-update tiles (lower 8 x 8 tiles of H, row blocks paired (p, nrb-1-p) so that every warp has the same share):
+    // up to four full tiles (slots 0..3) and, for nrb == 8 (36 tiles over 8 warps = 4.5 each), one k-half of a tile
+    // shared by the two warps of a pair (slot 4; the halves are added in the end phase).  A slot reads the A fragment of
+    // row block rA (a1) or rB (a2); unused slots compute a discarded dummy tile, so the loops carry no predicates.
+    //   rk[0], rk[1]: rA, rB;   rk[2 + s]: column block | uses-a2 << 8 | valid << 9;   rk[7]: first k of slot 4 (32 k-steps) or -1
+    if (lane == 0) {
+        int rA = 0, rB = 0, cb[5] = {0, 0, 0, 0, 0}, k4 = -1;
+        bool b2[5] = {false, false, false, false, false}, ok[5] = {false, false, false, false, false};
+        if (nrb == 8) {
+            const int p = warp < 4 ? warp : 7 - warp;
+            if (warp < 4) {      // row block p: columns 0..p;  row block 7-p: columns 0..2-p and the first k-half of 3-p
+                rA = p * 8; rB = (7 - p) * 8;
+                for (int s = 0; s < 4; ++s) { ok[s] = true; b2[s] = s > p; cb[s] = s > p ? s - (p + 1) : s; }
+                ok[4] = true; b2[4] = true; cb[4] = 3 - p; k4 = 0;
+            } else {             // row block 7-p (= warp): columns 4-p..7-p and the second k-half of column 3-p
+                rA = warp * 8; rB = rA;
+                for (int s = 0; s < 4; ++s) { ok[s] = true; cb[s] = 4 - p + s; }
+                ok[4] = true; cb[4] = 3 - p; k4 = 32;
+            }
+        } else if (active) {
+            const int partner = nrb - 1 - warp, share = (nrb + 2) >> 1;     // ceil((nrb + 1) / 2) <= 4 tiles per warp
+            int hA0 = 0, hB1 = 0;
+            if (warp < partner) hB1 = max(0, share - (warp + 1));
+            else if (warp > partner) hA0 = max(0, share - (partner + 1));
+            rA = warp * 8; rB = partner * 8;
+            int n = 0;
+            for (int t = hA0; t <= warp; ++t, ++n) { ok[n] = true; cb[n] = t; }
+            for (int t = 0; t < hB1; ++t, ++n) { ok[n] = true; b2[n] = true; cb[n] = t; }
+        }
+        fs->rk[warp][0] = rA; fs->rk[warp][1] = rB; fs->rk[warp][7] = k4;
+        for (int s = 0; s < 5; ++s) fs->rk[warp][2 + s] = cb[s] | (b2[s] ? 256 : 0) | (ok[s] ? 512 : 0);
     }
-    double accHA[4][2], accHB[4][2];      // at most 4 tiles per segment for every nrb <= 8
-    accT_zero<4>(accHA);
-    accT_zero<4>(accHB);
-    const int ar = lane >> 2, ac = 2 * (lane & 3);
+    // stash: H accumulators of slot s at st2[s * GPC_THREADS + tid] (double2), running sum k at sts[k * GPC_THREADS + tid]
+    double2* const st2 = reinterpret_cast<double2*>(fs->T1) + tid;
+    double* const sts = fs->T1 + 10 * GPC_THREADS + tid;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) st2[s * GPC_THREADS] = make_double2(0.0, 0.0);
+    sts[0] = sum_ve; sts[GPC_THREADS] = sum_da;                       // the pre-pass sums of this thread
+#pragma unroll
+    for (int k = 2; k < 6; ++k) sts[k * GPC_THREADS] = 0.0;           // [2] dk, [3] gv, [4] sk, [5] skr
     PROF_MARK(3);
     // Tile stream: the counts / scale factors of column tile t+1 travel by TMA (one 64 x 1 box of the gene-major [D][ldy]
-    // tensors per tile, double-buffered, mbarrier completion) while tile t is processed; the inputs X of tile t+1 are
-    // prefetched into registers.  Without descriptors (odd row pitch) y / scale are read with ordinary loads.
+    // tensors per tile, double-buffered, mbarrier completion) while tile t is processed; the inputs of the lane's column
+    // of tile t+1 are prefetched into registers.  Without descriptors (odd row pitch) y / scale are read with ordinary loads.
     const FzCfg& cf = fs->cfg;
     const bool tma = cf.tmY != nullptr;
     const bool has_scale = scale != nullptr;
@@ -557,117 +590,139 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    double xpre = 0.0;
-    if (tid < 64 * dd) xpre = (tid < min(64, N) * dd) ? cf.X[tid] : 0.0;
+    double xn0 = 0.0, xn1 = 0.0;
+    if (cg < N) { xn0 = cf.X[(size_t)cg * dd]; if (dd > 1) xn1 = cf.X[(size_t)cg * dd + 1]; }
     __syncthreads();
     if (tma && tid == 0) {
         fz_mbar_expect_tx(&fs->mbar[0], has_scale ? 1024u : 512u);
         fz_tma_row_tile(fs->ytile[0], cf.tmY, cf.n_off, cf.row, &fs->mbar[0]);
         if (has_scale) fz_tma_row_tile(fs->stile[0], cf.tmS, cf.n_off, cf.row, &fs->mbar[0]);
     }
-    if (tid < 64 * dd) fs->Xs[0][tid] = xpre;
+    double* __restrict__ const TA = fs->T0;
     int it = 0;
     for (int n0 = 0; n0 < N; n0 += 64, ++it) {
         const int nt = min(64, N - n0), bf = it & 1;
-        __syncthreads();                                   // tile it-1 is finished everywhere: its buffers may be refilled
-        const bool more = n0 + 64 < N;
-        if (more) {
+        const double x0 = xn0, x1 = xn1;
+        if (n0 + 64 < N) {
+            // buffers bf^1 were last read in the quadrature of tile it-1, which every warp left before the barriers of it-1
             if (tma && tid == 0) {
                 fz_mbar_expect_tx(&fs->mbar[bf ^ 1], has_scale ? 1024u : 512u);
                 fz_tma_row_tile(fs->ytile[bf ^ 1], cf.tmY, cf.n_off + n0 + 64, cf.row, &fs->mbar[bf ^ 1]);
                 if (has_scale) fz_tma_row_tile(fs->stile[bf ^ 1], cf.tmS, cf.n_off + n0 + 64, cf.row, &fs->mbar[bf ^ 1]);
             }
-            const int ntn = min(64, N - n0 - 64);
-            if (tid < 64 * dd) xpre = (tid < ntn * dd) ? cf.X[(size_t)(n0 + 64) * dd + tid] : 0.0;   // consumed at the end of the tile
+            const int cn = n0 + 64 + cg;
+            xn0 = cn < N ? cf.X[(size_t)cn * dd] : 0.0;
+            xn1 = (dd > 1 && cn < N) ? cf.X[(size_t)cn * dd + 1] : 0.0;
         }
-        if (!tma && tid >= 128 && tid < 192) {
-            const int c = tid - 128;
-            const bool v = c < nt;
-            fs->ytile[bf][c] = v ? y[n0 + c] : 0.0;
-            fs->stile[bf][c] = (v && has_scale) ? scale[n0 + c] : 1.0;
-        }
-        const double* Xcur = fs->Xs[bf];
-        // ---- Kuf tile: thread owns column c = tid & 63, rows (tid >> 6) + FZ_LPC t ---------------------------------
-        // The FZ_RPT squared distances of a thread go through one vectorised exp (independent chains, fastmath.cuh);
-        // padded rows / columns (Zs, Xs are zero there) are computed too and masked on the way out.
+        // ---- Gram entries of column cg in B-fragment order: bK[j] = Kuf[4 j + ak][cg] --------------------------------
+        // vectorised exp over eight entries at a time (independent chains, fastmath.cuh); padded rows / columns are masked
+        double bK[16];
         {
-            const int c = tid & 63, ib = tid >> 6;
-            const bool cv = c < nt;
+            const bool cv = cg < nt;
             const double var = kp.var;
             if (cf.kernel == GPC_CONST) {
 #pragma unroll
-                for (int t = 0; t < FZ_RPT; ++t) {
-                    const int i = ib + FZ_LPC * t;
-                    fs->T0[i * FZ_LD + c] = (cv && i < M) ? var : 0.0;
-                }
+                for (int j = 0; j < 16; ++j) bK[j] = (cv && 4 * j + ak < M) ? var : 0.0;
             } else {
-                const double* xc = Xcur + c * dd;
-                const double x0 = xc[0], x1 = dd > 1 ? xc[1] : 0.0;
                 const double ce = -0.5 * kp.inv_ls2;
-                double r2[FZ_RPT], ev[FZ_RPT];
 #pragma unroll
-                for (int t = 0; t < FZ_RPT; ++t) {
-                    const int i = ib + FZ_LPC * t;
-                    const double u = fs->Zs[i * dd] - x0;
-                    double r = u * u;
-                    if (dd > 1) { const double v = fs->Zs[i * dd + 1] - x1; r = fma(v, v, r); }
-                    r2[t] = r;
-                    ev[t] = ce * r;
-                }
-                gpc_exp_v<FZ_RPT>(ev, ev);
+                for (int h = 0; h < 2; ++h) {             // two halves of eight: bounds the live registers around the exp
+                    double r2[8], ev[8];
 #pragma unroll
-                for (int t = 0; t < FZ_RPT; ++t) {
-                    const int i = ib + FZ_LPC * t;
-                    const double kv = (cv && i < M) ? var * ev[t] : 0.0;
-                    fs->T0[i * FZ_LD + c] = kv;
-                    if (need_s) fs->T3[i * FZ_LD + c] = kv * r2[t];      // Kuf o R^2, for d/d lengthscale
+                    for (int j = 0; j < 8; ++j) {
+                        const int i = 4 * (8 * h + j) + ak;
+                        const double u = fs->Zs[i * dd] - x0;
+                        double r = u * u;
+                        if (dd > 1) { const double v = fs->Zs[i * dd + 1] - x1; r = fma(v, v, r); }
+                        r2[j] = r;
+                        ev[j] = ce * r;
+                    }
+                    gpc_exp_v<8>(ev, ev);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int i = 4 * (8 * h + j) + ak;
+                        const double kv = (cv && i < M) ? var * ev[j] : 0.0;
+                        bK[8 * h + j] = kv;
+                        if (need_s) fs->T3[i * FZ_LD + cg] = kv * r2[j];   // Kuf o R^2, for d/d lengthscale
+                    }
                 }
             }
         }
-        __syncthreads();
         PROF_MARK(4);
-        double acc[FZ_TPH][2], acc2[FZ_TPH][2];
-        // ---- A = Linv * Kuf (k <= row) -> T1 --------------------------------------------------------------------
-        if (active) {
-            accT_zero<FZ_TPH>(acc); accT_zero<FZ_TPH>(acc2);
-            warp_mmaT<false, false, FZ_TPH>(acc, fs->Linv, rA, fs->T0, 0, rA + 8, ctA);
-            warp_mmaT<false, false, FZ_TPH>(acc2, fs->Linv, rB, fs->T0, 0, rB + 8, ctB);
-            accT_store<FZ_TPH>(acc, fs->T1, rA, ctA);
-            accT_store<FZ_TPH>(acc2, fs->T1, rB, ctB);
+        if (it > 0) __syncthreads();      // every warp has left the rank update of the previous tile: T0 and gv2 may be rewritten
+        // ---- A = Linv * Kuf (k <= row): row block rb needs the k-steps j <= 2 rb + 1 --------------------------------
+        double accC[8][2];
+        {
+            double accA[8][2];
+            accT_zero<8>(accA);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+#pragma unroll
+                for (int rb = 0; rb < 8; ++rb) {
+                    if (rb >= (j >> 1) && rb < nrb) {
+                        const double a = fs->Linv[(rb * 8 + ar) * FZ_LD + 4 * j + ak];
+                        dmma884(accA[rb], a, bK[j]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int rb = 0; rb < 8; ++rb)
+                if (rb < nrb) *reinterpret_cast<double2*>(&TA[(rb * 8 + ar) * FZ_LD + cw + ac]) = make_double2(accA[rb][0], accA[rb][1]);
         }
-        __syncthreads();
+        __syncwarp();
         PROF_MARK(5);
-        // ---- C = W * A (full k-range) -> T2 ------------------------------------------------------------------------
-        if (active) {
-            accT_zero<FZ_TPH>(acc); accT_zero<FZ_TPH>(acc2);
-            warp_mmaT<false, false, FZ_TPH>(acc, fs->W, rA, fs->T1, 0, Mp, ctA);
-            warp_mmaT<false, false, FZ_TPH>(acc2, fs->W, rB, fs->T1, 0, Mp, ctB);
-            accT_store<FZ_TPH>(acc, fs->T2, rA, ctA);
-            accT_store<FZ_TPH>(acc2, fs->T2, rB, ctB);
+        // ---- C = W * A (full k-range) ---------------------------------------------------------------------------------
+        accT_zero<8>(accC);
+#pragma unroll 4
+        for (int k0 = 0; k0 < Mp; k0 += 4) {
+            const double b = TA[(k0 + ak) * FZ_LD + cw + ar];
+#pragma unroll
+            for (int rb = 0; rb < 8; ++rb) {
+                if (rb < nrb) {
+                    const double a = fs->W[(rb * 8 + ar) * FZ_LD + k0 + ak];
+                    dmma884(accC[rb], a, b);
+                }
+            }
         }
-        __syncthreads();
         PROF_MARK(6);
-        // ---- per-column statistics + quadrature: FZ_LPC adjacent lanes per column ---------------------------------
-        //   fmean = a . q_mu,  fvar = kdiag + a . (W a)
+        // ---- per-column statistics: fmean = a . q_mu, fvar = kdiag + a . (W a);  A is re-read from the slab -------------
+        double fm, s2;
+        {
+            double s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0;      // columns cw + ac, cw + ac + 1 over rows rb * 8 + ar
+#pragma unroll
+            for (int rb = 0; rb < 8; ++rb) {
+                if (rb < nrb) {
+                    const double q = fs->qmu[rb * 8 + ar];
+                    const double2 av = *reinterpret_cast<const double2*>(&TA[(rb * 8 + ar) * FZ_LD + cw + ac]);
+                    s1a = fma(av.x, q, s1a); s1b = fma(av.y, q, s1b);
+                    s2a = fma(av.x, accC[rb][0], s2a); s2b = fma(av.y, accC[rb][1], s2b);
+                }
+            }
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                s1a += __shfl_xor_sync(0xffffffffu, s1a, o); s1b += __shfl_xor_sync(0xffffffffu, s1b, o);
+                s2a += __shfl_xor_sync(0xffffffffu, s2a, o); s2b += __shfl_xor_sync(0xffffffffu, s2b, o);
+            }
+            if (need_s) {
+#pragma unroll
+                for (int rb = 0; rb < 8; ++rb)
+                    if (rb < nrb) *reinterpret_cast<double2*>(&fs->T2[(rb * 8 + ar) * FZ_LD + cw + ac]) = make_double2(accC[rb][0], accC[rb][1]);
+            }
+            // lane (ar, ak) continues with column cg = cw + ar: its sums sit in the lanes with ak' = ar >> 1, element ar & 1
+            const int src = ar >> 1;
+            const double f0 = __shfl_sync(0xffffffffu, s1a, src), f1 = __shfl_sync(0xffffffffu, s1b, src);
+            const double v0 = __shfl_sync(0xffffffffu, s2a, src), v1 = __shfl_sync(0xffffffffu, s2b, src);
+            fm = (ar & 1) ? f1 : f0;
+            s2 = (ar & 1) ? v1 : v0;
+        }
+        // ---- quadrature: the four lanes ak = 0..3 of column cg share its 20 nodes ------------------------------------
         if (tma) fz_mbar_wait(&fs->mbar[bf], (unsigned)(it >> 1) & 1u);      // y / scale of this tile have landed
         {
-            const int c = tid / FZ_LPC, part = tid % FZ_LPC;
-            double s1 = 0.0, s2 = 0.0;
-#pragma unroll
-            for (int t = 0; t < FZ_RPT; ++t) {
-                const int i = part + FZ_LPC * t;
-                if (i < Mp) {
-                    const double a = fs->T1[i * FZ_LD + c];
-                    s1 = fma(a, fs->qmu[i], s1);
-                    s2 = fma(a, fs->T2[i * FZ_LD + c], s2);
-                }
-            }
-#pragma unroll
-            for (int o = 1; o < FZ_LPC; o <<= 1) {
-                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-            }
-            const double fm = s1, fv = kdiag + s2, yy = fs->ytile[bf][c];
+            const int c = cg, part = ak;
+            const double fv = kdiag + s2;
+            double yy, sc = 1.0;
+            if (tma) { yy = fs->ytile[bf][c]; if (has_scale) sc = fs->stile[bf][c]; }
+            else { yy = c < nt ? y[n0 + c] : 0.0; if (has_scale && c < nt) sc = scale[n0 + c]; }
             double ve = 0.0, gm = 0.0, gz = 0.0, da = 0.0, dk = 0.0;
             bool poison = false;
             if (c < nt) {
@@ -680,13 +735,14 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
                     }
                 } else {
                     const double sd = sqrt(fv);
-                    const LikPart o = (cf.lik == GPC_NB) ? lik_nodes_nb<FZ_LPC>(lp, fm, sd, yy, has_scale ? fs->stile[bf][c] : 1.0, part)
+                    const LikPart o = (cf.lik == GPC_NB) ? lik_nodes_nb<FZ_LPC>(lp, fm, sd, yy, sc, part)
                                                          : lik_nodes<FZ_LPC>(lp, fm, sd, yy, 0.0, part);
                     ve = o.ve; gm = o.gm; gz = o.gz; da = o.da; dk = o.dk; poison = o.poison;
                 }
             }
             if (poison) { gm = NAN; gz = NAN; dk = NAN; }
-            sum_ve += ve; sum_da += da; sum_dk += dk;
+            sts[0] += ve; sts[GPC_THREADS] += da;
+            if (cf.lik == GPC_ZINB) sts[2 * GPC_THREADS] += dk;
 #pragma unroll
             for (int o = 1; o < FZ_LPC; o <<= 1) {
                 gm += __shfl_xor_sync(0xffffffffu, gm, o);
@@ -698,103 +754,121 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
                 else gm = 0.0;
                 fs->gm[c] = gm;
                 fs->gv2[c] = 2.0 * gv;
-                sum_gv += gv;
+                sts[3 * GPC_THREADS] += gv;
                 // <Abar, A> = sum_n g_m fmean + 2 g_v a.(W a)   (= <S, Kuf>: d/d variance of the cross-covariance)
-                sum_sk += gm * fm + 2.0 * gv * s2;
+                sts[4 * GPC_THREADS] += gm * fm + 2.0 * gv * s2;
             }
         }
-        __syncthreads();
+        __syncwarp();
         PROF_MARK(7);
-        // ---- gq += A gm;  S = u gm^T + (Linv^T C) diag(2 gv) in registers -> <S o Kuf, R^2> ---------------------------
-        if (active) {
-            if (need_s) {
-                accT_zero<FZ_TPH>(acc); accT_zero<FZ_TPH>(acc2);
-                warp_mmaT<true, false, FZ_TPH>(acc, fs->Linv, rA, fs->T2, rA, Mp, ctA);
-                warp_mmaT<true, false, FZ_TPH>(acc2, fs->Linv, rB, fs->T2, rB, Mp, ctB);
-            }
-            PROF_MARK(10);
-            double gqa = 0.0, gqb = 0.0;
+        // ---- S = u gm^T + (Linv^T C) diag(2 gv) in registers -> <S o Kuf, R^2>;  gq += A gm ----------------------------
+        if (need_s) {
+            accT_zero<8>(accC);
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int r = (half ? rB : rA) + ar;
-                double gql = 0.0;
-                const double ur = fs->uvec[r];
+            for (int j = 0; j < 16; ++j) {
+                if (4 * j < Mp) {
+                    const double b = fs->T2[(4 * j + ak) * FZ_LD + cw + ar];
 #pragma unroll
-                for (int t = 0; t < FZ_TPH; ++t) {
-                    const int c = ((half ? ctB : ctA) + t) * 8 + ac;
-                    const double2 a = *reinterpret_cast<const double2*>(&fs->T1[r * FZ_LD + c]);
-                    const double g0 = fs->gm[c], g1 = fs->gm[c + 1];
-                    gql = fma(a.x, g0, gql);
-                    gql = fma(a.y, g1, gql);
-                    if (need_s) {
-                        const double w0 = fs->gv2[c], w1 = fs->gv2[c + 1];
-                        const double p0 = half ? acc2[t][0] : acc[t][0], p1 = half ? acc2[t][1] : acc[t][1];
-                        const double2 kr = *reinterpret_cast<const double2*>(&fs->T3[r * FZ_LD + c]);
-                        sum_skr = fma(fma(p0, w0, ur * g0), kr.x, sum_skr);
-                        sum_skr = fma(fma(p1, w1, ur * g1), kr.y, sum_skr);
-                    }
-                }
-                if (half) gqb = gql; else gqa = gql;
-            }
-            gqa += __shfl_xor_sync(0xffffffffu, gqa, 1); gqa += __shfl_xor_sync(0xffffffffu, gqa, 2);
-            gqb += __shfl_xor_sync(0xffffffffu, gqb, 1); gqb += __shfl_xor_sync(0xffffffffu, gqb, 2);
-            // each (row, column group) partial sum has exactly one writer
-            if ((lane & 3) == 0) { fs->gq[0][rA + ar] += gqa; fs->gq[1][rB + ar] += gqb; }
-            PROF_MARK(11);
-            // ---- H += (A diag(2 gv)) A^T, lower tiles ---------------------------------------------------------------
-            {
-                const int ak = lane & 3;
-#pragma unroll 4
-                for (int k0 = 0; k0 < 64; k0 += 4) {
-                    const double sc = fs->gv2[k0 + ak];
-                    const double a1 = fs->T1[(rA + ar) * FZ_LD + k0 + ak] * sc;
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        if (hA0 + t < hA1) {
-                            const double bb = fs->T1[((hA0 + t) * 8 + ar) * FZ_LD + k0 + ak];
-                            dmma884(accHA[t], a1, bb);
-                        }
-                    }
-                    if (hB1 > 0) {
-                        const double a2 = fs->T1[(rB + ar) * FZ_LD + k0 + ak] * sc;
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            if (t < hB1) {
-                                const double bb = fs->T1[(t * 8 + ar) * FZ_LD + k0 + ak];
-                                dmma884(accHB[t], a2, bb);
-                            }
+                    for (int rb = 0; rb < 8; ++rb) {
+                        if (rb <= (j >> 1) && rb < nrb) {
+                            const double a = fs->Linv[(4 * j + ak) * FZ_LD + rb * 8 + ar];
+                            dmma884(accC[rb], a, b);
                         }
                     }
                 }
             }
         }
-        if (more && tid < 64 * dd) fs->Xs[bf ^ 1][tid] = xpre;
+        PROF_MARK(10);
+        {
+            const double g0 = fs->gm[cw + ac], g1 = fs->gm[cw + ac + 1];
+            const double w0 = fs->gv2[cw + ac], w1 = fs->gv2[cw + ac + 1];
+            double skr = 0.0;
+#pragma unroll
+            for (int rb = 0; rb < 8; ++rb) {
+                if (rb < nrb) {
+                    const int r = rb * 8 + ar;
+                    const double2 av = *reinterpret_cast<const double2*>(&TA[r * FZ_LD + cw + ac]);
+                    double gp = fma(av.y, g1, av.x * g0);
+                    gp += __shfl_xor_sync(0xffffffffu, gp, 1);
+                    gp += __shfl_xor_sync(0xffffffffu, gp, 2);
+                    if (ak == 0) fs->gqw[warp][r] += gp;
+                    if (need_s) {
+                        const double ur = fs->uvec[r];
+                        const double2 kr = *reinterpret_cast<const double2*>(&fs->T3[r * FZ_LD + cw + ac]);
+                        skr = fma(fma(accC[rb][0], w0, ur * g0), kr.x, skr);
+                        skr = fma(fma(accC[rb][1], w1, ur * g1), kr.y, skr);
+                    }
+                }
+            }
+            if (need_s) sts[5 * GPC_THREADS] += skr;
+        }
+        PROF_MARK(11);
+        __syncthreads();                  // the tile's A and 2 g_v are complete
+        // ---- H += (A diag(2 gv)) A^T, lower tiles ---------------------------------------------------------------------
+        {
+            const int* rk = fs->rk[warp];
+            const int lo = ar * FZ_LD + ak;
+            const int offA = rk[0] * FZ_LD + lo, offB = rk[1] * FZ_LD + lo, k4b = rk[7] < 0 ? 64 : rk[7], k4e = rk[7] < 0 ? 64 : rk[7] + 32;
+            int s_off[5];
+            bool s_b[5];
+#pragma unroll
+            for (int s = 0; s < 5; ++s) { const int v = rk[2 + s]; s_off[s] = (v & 255) * 8 * FZ_LD + lo; s_b[s] = (v & 256) != 0; }
+            double accH[5][2];
+#pragma unroll
+            for (int s = 0; s < 5; ++s) { const double2 v = st2[s * GPC_THREADS]; accH[s][0] = v.x; accH[s][1] = v.y; }
+            auto step = [&](int k0, bool with4) {
+                const double sc = fs->gv2[k0 + ak];
+                const double a1 = TA[offA + k0] * sc, a2 = TA[offB + k0] * sc;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) dmma884(accH[s], s_b[s] ? a2 : a1, TA[s_off[s] + k0]);
+                if (with4) dmma884(accH[4], s_b[4] ? a2 : a1, TA[s_off[4] + k0]);
+            };
+#pragma unroll 2
+            for (int k0 = 0; k0 < k4b; k0 += 4) step(k0, false);
+#pragma unroll 2
+            for (int k0 = k4b; k0 < k4e; k0 += 4) step(k0, true);
+#pragma unroll 2
+            for (int k0 = k4e; k0 < 64; k0 += 4) step(k0, false);
+#pragma unroll
+            for (int s = 0; s < 5; ++s) st2[s * GPC_THREADS] = make_double2(accH[s][0], accH[s][1]);
+        }
         PROF_MARK(8);
     }
-    __syncthreads();
     // ---- end phase ------------------------------------------------------------------------------------------------
-    // H (symmetric) -> T1 (every tile of the nrb x nrb block grid has exactly one owner, mirrors included);  Lq -> T0
+    // H (symmetric) -> T1 (every tile of the nrb x nrb block grid has exactly one owner, mirrors included; the tile shared
+    // by a warp pair is written by its first owner and completed by the second after a barrier);  Lq -> T0;  the warps'
+    // gq sums -> gq in a fixed order
+    double accH[5][2];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) { const double2 v = st2[s * GPC_THREADS]; accH[s][0] = v.x; accH[s][1] = v.y; }
+    sum_ve = sts[0]; sum_da = sts[GPC_THREADS]; sum_dk = sts[2 * GPC_THREADS];
+    sum_gv = sts[3 * GPC_THREADS]; sum_sk = sts[4 * GPC_THREADS]; sum_skr = sts[5 * GPC_THREADS];
+    __syncthreads();                      // the stash (T1) and the last A tile (T0) have been read everywhere
     for (int idx = tid; idx < Mp * 64; idx += GPC_THREADS) {
         const int i = idx >> 6, j = idx & 63;
         fs->T0[i * FZ_LD + j] = (i < M && j <= i) ? lq_packed[tri_index(i, j)] : 0.0;
     }
-    if (active) {
+    const int* rk = fs->rk[warp];
+    auto h_store = [&](int s, bool add) {
+        const int v = rk[2 + s], cb = v & 255, rb = ((v & 256) ? rk[1] : rk[0]) >> 3;
+        const int i = (rb << 3) + ar, j = cb * 8 + ac;
+        double v0 = accH[s][0], v1 = accH[s][1];
+        if (add) { v0 += fs->T1[i * FZ_LD + j]; v1 += fs->T1[i * FZ_LD + j + 1]; }
+        fs->T1[i * FZ_LD + j] = v0; fs->T1[i * FZ_LD + j + 1] = v1;
+        if (cb < rb) { fs->T1[j * FZ_LD + i] = v0; fs->T1[(j + 1) * FZ_LD + i] = v1; }
+    };
+    const bool s4_first = (rk[6] & 512) && rk[7] <= 0, s4_second = (rk[6] & 512) && rk[7] > 0;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            if (hA0 + t < hA1) {
-                const int i = rA + ar, j = (hA0 + t) * 8 + ac;
-                fs->T1[i * FZ_LD + j] = accHA[t][0]; fs->T1[i * FZ_LD + j + 1] = accHA[t][1];
-                if (hA0 + t < pr) { fs->T1[j * FZ_LD + i] = accHA[t][0]; fs->T1[(j + 1) * FZ_LD + i] = accHA[t][1]; }
-            }
-        }
+    for (int s = 0; s < 4; ++s)
+        if (rk[2 + s] & 512) h_store(s, false);
+    if (s4_first) h_store(4, false);
+    __syncthreads();
+    if (s4_second) h_store(4, true);
+    if (tid < 64) {
+        double v = 0.0;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            if (t < hB1) {
-                const int i = rB + ar, j = t * 8 + ac;
-                fs->T1[i * FZ_LD + j] = accHB[t][0]; fs->T1[i * FZ_LD + j + 1] = accHB[t][1];
-                fs->T1[j * FZ_LD + i] = accHB[t][0]; fs->T1[(j + 1) * FZ_LD + i] = accHB[t][1];   // t < partner: off-diagonal
-            }
-        }
+        for (int w = 0; w < FZ_NW; ++w) v += fs->gqw[w][tid];
+        fs->gq[tid] = v;
     }
     __syncthreads();
     {
@@ -813,7 +887,7 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
                 for (int ct = 0; ct < 8; ++ct) {
                     const int j = ct * 8 + ac;
                     if (ct < nrb) {
-                        const double g0 = fs->gq[0][j] + fs->gq[1][j], g1 = fs->gq[0][j + 1] + fs->gq[1][j + 1];
+                        const double g0 = fs->gq[j], g1 = fs->gq[j + 1];
                         *reinterpret_cast<double2*>(&fs->T3[(r0 + ar) * FZ_LD + j]) =
                             make_double2(fma(qm, g0, acc[ct][0]), fma(qm, g1, acc[ct][1]));
                     }
@@ -834,7 +908,7 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
         }
     }
     if (tid < M) {
-        grad[GPC_NHYP + tid] = (fs->gq[0][tid] + fs->gq[1][tid]) - fs->qmu[tid];
+        grad[GPC_NHYP + tid] = fs->gq[tid] - fs->qmu[tid];
         acc9[6] = fs->qmu[tid] * fs->qmu[tid];
     }
     cta_sum_n<9>(acc9, fs->red2);
@@ -945,5 +1019,6 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
 
 __device__ __noinline__ int eval_svgp_fused(const ModelDev& md, const double* Z, const double* y, const double* scale,
                                const double* theta, double* grad, double* f_out, const SlotWs& ws, FusedSmem* fs) {
-    return eval_svgp_fused_impl(md, Z, y, scale, theta, grad, f_out, ws, fs);
+    if (md.M > 56) return eval_svgp_fused_impl<8>(md, Z, y, scale, theta, grad, f_out, ws, fs);
+    return eval_svgp_fused_impl<0>(md, Z, y, scale, theta, grad, f_out, ws, fs);
 }
