@@ -505,8 +505,10 @@ static cudaError_t GPC_KNAME(v_launch_eval)(const void* a, int grid, int nmax, c
 static int GPC_KNAME(v_read_prof)(unsigned long long* out16) {
     cudaDeviceSynchronize();
     if (cudaMemcpyFromSymbol(out16, g_phase_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(out16 + 16, g_opt_prof, sizeof(unsigned long long) * 8) != cudaSuccess) return -1;   // out16: 24 entries
     unsigned long long z[16] = {0};
     cudaMemcpyToSymbol(g_phase_prof, z, sizeof(z));
+    cudaMemcpyToSymbol(g_opt_prof, z, sizeof(unsigned long long) * 8);
     return 0;
 }
 #endif

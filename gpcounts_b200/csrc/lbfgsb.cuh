@@ -35,7 +35,11 @@ struct OptSmem {
     double WN[2 * GPC_MMAX][2 * GPC_MMAX];   // upper-triangular LEL^T factor of the middle matrix
     double wv[2 * GPC_MMAX];
     double dots[GPC_MMAX][6];          // per memory vector: S.d, Y.d, S.r, Y.r, S.g, Y.g
+#ifndef GPC_SMALL_ONLY
+    double dotq[4][GPC_MMAX][6];       // the same over one quarter of the elements (summed in a fixed order)
+#endif
     double T[GPC_MMAX][GPC_MMAX];      // formt scratch
+    double rd[2 * GPC_MMAX];           // 1 / diag of the LEL^T factor in WN (formk_free), used by subsm_solve
     int info;
     int info_dir;                      // outcome of the direction solve (formk / subsm) done at the end of an iteration
     double red[64];                    // CTA reduction scratch of the optimiser
@@ -191,52 +195,76 @@ __device__ __forceinline__ int dcsrch_step(DcsrchState& s, double f, double g) {
 // The limited-memory matrices are at most 20 x 20; warp 0 works on them cooperatively in shared memory (the rest
 // of the CTA waits at the next barrier).  All routines must be called by every lane of one warp.
 
-// Upper Cholesky A = R^T R of the leading n x n block (LINPACK dpofa semantics: 0 or the failing pivot index).
-__device__ int warp_chol_upper(double* A, int lda, int n) {
+// Upper Cholesky A = R^T R of the leading n x n block, n <= GPC_MMAX (LINPACK dpofa semantics: 0 or the failing pivot
+// index); rdiag, if given, receives 1 / R[k][k].  Right-looking; per pivot every lane fetches the operands of its trailing
+// entries BEFORE the pivot's rsqrt chain (they do not depend on it), so a pivot step costs one shared-memory round trip
+// plus the rsqrt chain instead of three round trips, a square root and a division.
+__device__ int warp_chol_upper(double* A, int lda, int n, double* rdiag) {
     const int lane = threadIdx.x & 31;
+    constexpr int NQ = ((GPC_MMAX - 1) * (GPC_MMAX - 1) + 31) / 32;     // trailing entries per lane (square enumeration)
     for (int k = 0; k < n; ++k) {
         __syncwarp();
         const double akk = A[k * lda + k];
-        if (!(akk > 0.0)) return k + 1;
-        const double r = sqrt(akk);
-        __syncwarp();
-        if (lane == 0) A[k * lda + k] = r;
-        for (int j = k + 1 + lane; j < n; j += 32) A[k * lda + j] /= r;
-        __syncwarp();
         const int rem = n - k - 1;
         const unsigned inv = rem > 0 ? (65536u + rem - 1) / rem : 0u;   // exact idx / rem for idx < rem^2, rem <= 20
-        for (int idx = lane; idx < rem * rem; idx += 32) {
-            const int q = (int)(((unsigned)idx * inv) >> 16);
-            const int i = k + 1 + q, j = k + 1 + (idx - q * rem);
-            if (j >= i) A[i * lda + j] -= A[k * lda + i] * A[k * lda + j];
+        double aki[NQ], akj[NQ], aij[NQ];
+        int off[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int idx = lane + 32 * q;
+            const int d = (int)(((unsigned)idx * inv) >> 16);
+            const int i = k + 1 + d, j = k + 1 + (idx - d * rem);
+            const bool on = idx < rem * rem && j >= i;
+            off[q] = on ? i * lda + j : -1;
+            aki[q] = on ? A[k * lda + i] : 0.0;
+            akj[q] = on ? A[k * lda + j] : 0.0;
+            aij[q] = on ? A[i * lda + j] : 0.0;
         }
+        const double akl = lane < rem ? A[k * lda + k + 1 + lane] : 0.0;
+        if (!(akk > 0.0)) return k + 1;
+        const double rs = gpc_rsqrt(akk);
+        double r = akk * rs;
+        r = fma(fma(-r, r, akk), 0.5 * rs, r);                          // sqrt(akk)
+        __syncwarp();                                                   // every lane holds its operands: row k may be rewritten
+        if (lane == 0) { A[k * lda + k] = r; if (rdiag) rdiag[k] = rs; }
+        if (lane < rem) A[k * lda + k + 1 + lane] = akl * rs;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+            if (off[q] >= 0) A[off[q]] = fma(-(aki[q] * rs), akj[q] * rs, aij[q]);
     }
     __syncwarp();
     return 0;
 }
 
-// formk for the all-free case: builds and factors WN (upper triangle). 0 on success.
+// formk for the all-free case: builds and factors WN (upper triangle). 0 on success.  os->rd receives 1 / diag.
 __device__ int formk_free(OptSmem* os, int col, double theta) {
     const int L2 = 2 * GPC_MMAX, lane = threadIdx.x & 31;
     double* WN = &os->WN[0][0];
+    const double ith = 1.0 / theta;
     for (int idx = lane; idx < col * col; idx += 32) {
         const int iy = idx / col, jy = idx % col;
         if (jy <= iy) {
-            WN[jy * L2 + iy] = os->YY[iy][jy] / theta + (jy == iy ? os->SY[iy][iy] : 0.0);   // Y'Y / theta + D
+            WN[jy * L2 + iy] = os->YY[iy][jy] * ith + (jy == iy ? os->SY[iy][iy] : 0.0);     // Y'Y / theta + D
             WN[(col + jy) * L2 + col + iy] = 0.0;                                            // theta * S'AA'S = 0
         }
         WN[jy * L2 + col + iy] = (jy >= iy) ? os->RZ[iy][jy] : 0.0;                           // R_z' (and -L_a' = 0)
     }
     __syncwarp();
-    int info = warp_chol_upper(WN, L2, col);
+    int info = warp_chol_upper(WN, L2, col, os->rd);
     if (info != 0) return -1;
-    // columns of block (1,2): solve R1^T x = b  (dtrsl job 11), one lane per column
+    // columns of block (1,2): solve R1^T x = b  (dtrsl job 11), one lane per column, the column in registers
     if (lane < col) {
         const int js = col + lane;
-        for (int i = 0; i < col; ++i) {
-            double t = WN[i * L2 + js];
-            for (int k = 0; k < i; ++k) t -= WN[k * L2 + i] * WN[k * L2 + js];
-            WN[i * L2 + js] = t / WN[i * L2 + i];
+        double x[GPC_MMAX];
+#pragma unroll
+        for (int i = 0; i < GPC_MMAX; ++i) {
+            if (i < col) {
+                double t = WN[i * L2 + js];
+#pragma unroll
+                for (int k = 0; k < i; ++k) t = fma(-WN[k * L2 + i], x[k], t);
+                x[i] = t * os->rd[i];
+                WN[i * L2 + js] = x[i];
+            }
         }
     }
     __syncwarp();
@@ -249,7 +277,7 @@ __device__ int formk_free(OptSmem* os, int col, double theta) {
         }
     }
     __syncwarp();
-    info = warp_chol_upper(WN + col * L2 + col, L2, col);
+    info = warp_chol_upper(WN + col * L2 + col, L2, col, os->rd + col);
     if (info != 0) return -2;
     return 0;
 }
@@ -267,30 +295,37 @@ __device__ int formt_check(OptSmem* os, int col, double theta) {
         }
     }
     __syncwarp();
-    return warp_chol_upper(T, GPC_MMAX, col);
+    return warp_chol_upper(T, GPC_MMAX, col, nullptr);
 }
 
-// subsm middle solve: wv <- K^-1 wv through the LEL^T factor (column-oriented substitutions).
+// subsm middle solve: wv <- K^-1 wv through the LEL^T factor (column-oriented substitutions).  Lane k keeps wv[k] in a
+// register (2 col <= 20 < 32), the pivot value travels by shuffle and the matrix row of the next step is fetched while the
+// current one is applied: a step is shuffle + multiply-add instead of two warp barriers, a division and two round trips
+// through shared memory.  os->rd holds 1 / diag of the factor (formk_free).
 __device__ void subsm_solve(OptSmem* os, int col) {
     const int L2 = 2 * GPC_MMAX, c2 = 2 * col, lane = threadIdx.x & 31;
-    double* WN = &os->WN[0][0];
-    double* wv = os->wv;
+    const double* WN = &os->WN[0][0];
+    const bool in = lane < c2;
+    double w = in ? os->wv[lane] : 0.0;
+    const double rdl = in ? os->rd[lane] : 0.0;
+    double un = in ? WN[lane] : 0.0;                      // U[0][lane]
     for (int i = 0; i < c2; ++i) {                       // U^T x = b
-        __syncwarp();
-        const double xi = wv[i] / WN[i * L2 + i];
-        __syncwarp();
-        if (lane == 0) wv[i] = xi;
-        for (int k = i + 1 + lane; k < c2; k += 32) wv[k] -= WN[i * L2 + k] * xi;
+        const double u = un;
+        if (i + 1 < c2) un = in ? WN[(i + 1) * L2 + lane] : 0.0;
+        const double xi = __shfl_sync(0xffffffffu, w * rdl, i);
+        if (lane == i) w = xi;
+        else if (lane > i) w = fma(-u, xi, w);
     }
-    __syncwarp();
-    if (lane < col) wv[lane] = -wv[lane];
+    if (lane < col) w = -w;
+    un = in ? WN[lane * L2 + c2 - 1] : 0.0;               // U[lane][c2 - 1]
     for (int i = c2 - 1; i >= 0; --i) {                  // U x = b
-        __syncwarp();
-        const double xi = wv[i] / WN[i * L2 + i];
-        __syncwarp();
-        if (lane == 0) wv[i] = xi;
-        for (int k = lane; k < i; k += 32) wv[k] -= WN[k * L2 + i] * xi;
+        const double u = un;
+        if (i > 0) un = in ? WN[lane * L2 + i - 1] : 0.0;
+        const double xi = __shfl_sync(0xffffffffu, w * rdl, i);
+        if (lane == i) w = xi;
+        else if (lane < i) w = fma(-u, xi, w);
     }
+    if (in) os->wv[lane] = w;
     __syncwarp();
 }
 
@@ -386,7 +421,18 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
     int col = 0, head = 0;
     double theta = 1.0;
     bool updated = false;      // a new pair was stored since the last formk
+#if defined(GPC_PHASE_PROF) && !defined(GPC_DENSE_ONLY) && !defined(GPC_SMALL_ONLY)
+    long long op_t = clock64(), op_acc[6] = {0, 0, 0, 0, 0, 0};
+#define OPROF(k) do { const long long t_ = clock64(); op_acc[k] += t_ - op_t; op_t = t_; } while (0)
+#define OPROF_RESET do { op_t = clock64(); } while (0)
+#define OPROF_FLUSH do { if (threadIdx.x == 0) { for (int q_ = 0; q_ < 6; ++q_) atomicAdd(&g_opt_prof[q_], (unsigned long long)op_acc[q_]); atomicAdd(&g_opt_prof[7], (unsigned long long)nit); } } while (0)
+#else
+#define OPROF(k)
+#define OPROF_RESET
+#define OPROF_FLUSH
+#endif
     while (true) {
+        OPROF_RESET;
         // ------------------------------------------------------------------ search direction (+ line-search set-up)
         // one pass: d = z - x, dtd, g.d, save (x, g) as (xold, gold); after the first iteration the first trial
         // point is z itself (stp = 1), so it is written in the same pass
@@ -455,6 +501,7 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
             }
         }
         cta_sum_n<2>(acc2, os->red);
+        OPROF(0);
         // ------------------------------------------------------------------ line search (lnsrlb)
         const double dtd = acc2[0];
         const double dnorm = sqrt(dtd);
@@ -481,9 +528,11 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
                     }
                     __syncthreads();
                 }
+                OPROF(1);
                 if (eval_loss(md, Z, y, scale, ws, sm, f, res.eval_cycles) != GPC_ST_OK) {
                     res.task = TASK_CHOL; res.nit = nit; res.nfev = nfev; return res;
                 }
+                OPROF_RESET;
                 // one pass: g <- -grad, g.d, max|g|, |g - gold|^2
                 double a3[2] = {0.0, 0.0};
                 double mx = 0.0;
@@ -515,6 +564,7 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
                 gd = a3[0]; rr = a3[1]; gmax = mx;
                 trace_eval(tr, f, stp, gd, ws.x, ws.g, P, os->red);
                 const int t = dcsrch_step(ls, f, gd);
+                OPROF(2);
                 if (t != 0) break;
                 if (ifun >= opt.maxls) { ls_failed = true; break; }
             }
@@ -597,11 +647,14 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
             updated = true;
         }
         __syncthreads();
+        OPROF(3);
         // dots of every memory pair with the new s (= d), y (= gold) and the new gradient g
+#ifdef GPC_SMALL_ONLY
+        // small-N instantiation (P <= 1228, two warps, vectors in shared memory): one warp per pair
         for (int j = warp; j < col; j += GPC_THREADS / 32) {
             const size_t slot = (size_t)((head + j) % m) * P;
             double a[6] = {0, 0, 0, 0, 0, 0};
-            for (int i0 = lane; i0 < P; i0 += 4 * 32) {           // twenty independent loads per step, same summation order
+            for (int i0 = lane; i0 < P; i0 += 4 * 32) {           // twenty independent loads per step
                 double sv[4], yv[4], dv[4], rv[4], gv[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -624,7 +677,49 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
             if (lane == 0)
                 for (int q = 0; q < 6; ++q) os->dots[j][q] = a[q];
         }
+#else
+        // Work items (pair j, quarter q of the elements) are dealt to the warps round-robin: with ten pairs on eight warps a
+        // warp-per-pair split leaves two warps with twice the work of the others, and every step of the element loop is an L2
+        // round trip (the vectors live in the slot) - thirty independent loads per step here.
+        {
+            const int PQ = (((P + 3) >> 2) + 31) & ~31;           // elements per quarter (multiple of the warp size)
+            for (int item = warp; item < 4 * col; item += GPC_THREADS / 32) {
+                const int j = item >> 2, qq = item & 3;
+                const size_t slot = (size_t)((head + j) % m) * P;
+                const int e1 = min(P, (qq + 1) * PQ);
+                double a[6] = {0, 0, 0, 0, 0, 0};
+                for (int i0 = qq * PQ + lane; i0 < e1; i0 += 6 * 32) {
+                    double sv[6], yv[6], dv[6], rv[6], gv[6];
+#pragma unroll
+                    for (int u = 0; u < 6; ++u) {
+                        const int i = i0 + u * 32;
+                        const bool in = i < e1;
+                        sv[u] = in ? ws.WS[slot + i] : 0.0; yv[u] = in ? ws.WY[slot + i] : 0.0;
+                        dv[u] = in ? ws.d[i] : 0.0; rv[u] = in ? ws.gold[i] : 0.0; gv[u] = in ? ws.g[i] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 6; ++u) {
+                        if (i0 + u * 32 < e1) {
+                            a[0] = fma(sv[u], dv[u], a[0]); a[1] = fma(yv[u], dv[u], a[1]);
+                            a[2] = fma(sv[u], rv[u], a[2]); a[3] = fma(yv[u], rv[u], a[3]);
+                            a[4] = fma(sv[u], gv[u], a[4]); a[5] = fma(yv[u], gv[u], a[5]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 6; ++q) a[q] = warp_sum(a[q]);
+                if (lane == 0)
+                    for (int q = 0; q < 6; ++q) os->dotq[qq][j][q] = a[q];
+            }
+            __syncthreads();
+            if (tid < 6 * col) {
+                const int j = tid / 6, q = tid % 6;
+                os->dots[j][q] = ((os->dotq[0][j][q] + os->dotq[1][j][q]) + os->dotq[2][j][q]) + os->dotq[3][j][q];
+            }
+        }
+#endif
         __syncthreads();
+        OPROF(4);
         if (!skip && warp == 0) {
             const int c = col - 1;
             if (lane < col) {
@@ -670,7 +765,9 @@ __device__ OptResult lbfgsb_minimize(const ModelDev& md, const double* Z, const 
             __syncthreads();
             if (info != 0) { col = 0; head = 0; theta = 1.0; updated = false; }
         }
+        OPROF(5);
     }
+    OPROF_FLUSH;
     res.nit = nit;
     res.nfev = nfev;
     res.f = f;

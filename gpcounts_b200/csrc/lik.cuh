@@ -5,6 +5,7 @@
 #pragma once
 #include <math.h>
 #include "../../include/gpcounts_b200.h"
+#include "fastmath.cuh"
 
 #define GPC_NGH 20
 
@@ -39,14 +40,41 @@ __device__ __forceinline__ double digamma_pos(double x) {
     return r + log(x) - 0.5 * xi - s;
 }
 
+// FAST: lgamma(k) / digamma(k) from the branch-free routine of fastmath.cuh.  An evaluator must take lgamma(k + y) and
+// lgamma(k) from the SAME implementation: at alpha -> 0 (k = 1/alpha ~ 1e39 on wild line-search trial points) k + y == k
+// in FP64 and the reference's lgamma(k + y) - lgamma(k) is exactly 0, whereas two implementations differ by
+// ~1e-16 * k log k ~ 1e25 and hand the line search a garbage objective.
+template <bool FAST = false>
 __device__ __forceinline__ void lik_setup(LikParams& lp, int lik, double alpha, double km) {
     lp.lik = lik;
     lp.alpha = alpha;
     lp.km = km;
     lp.k = 1.0 / alpha;
     lp.log_alpha = log(alpha);
-    lp.lgamma_k = lgamma(lp.k);
-    lp.digamma_k = digamma_pos(lp.k);
+    if (FAST) {
+        const double xa[1] = {lp.k};
+        double lg[1], dg[1];
+        gpc_lgamma_digamma_v<1>(xa, lg, dg);
+        lp.lgamma_k = lg[0];
+        lp.digamma_k = dg[0];
+    } else {
+        lp.lgamma_k = lgamma(lp.k);
+        lp.digamma_k = digamma_pos(lp.k);
+    }
+}
+
+// IEEE corner cases of the reference's NB log-density  Y log(m / (m + k)) - k log(1 + m alpha)
+// (NegativeBinomialLikelihood.py:37-48) that the fused form  y (log m + log alpha - lt) - k lt  does not reproduce:
+//   m = +inf (exp overflow):  log(inf / inf) = NaN                                   -> l = NaN (the gradients are NaN already)
+//   m = 0    (exp underflow): Y log(0) = -inf for Y > 0, 0 * -inf = NaN for Y = 0;   TensorFlow's d/dF = (..) * m = inf * 0 = NaN
+// They occur on wild line-search trial points and decide how SciPy's line search goes on (NaN objective: the step is
+// extended until 20 evaluations are spent, the BFGS memory is reset and the fit continues; +inf objective with a NaN
+// slope: retreat to the current iterate and stop), so they are reproduced rather than smoothed over.
+__device__ __forceinline__ void nb_corner_cases(double m, double y, double& l, double& dl) {
+    const bool m_inf = m > 1.7976931348623157e308, m_zero = m == 0.0;
+    l = m_inf ? NAN : l;
+    l = m_zero ? (y == 0.0 ? NAN : -INFINITY) : l;
+    dl = m_zero ? NAN : dl;
 }
 
 // y: count, s: scale factor (1 if none), lgy1 = lgamma(y + 1)
@@ -74,9 +102,10 @@ __device__ LikPoint lik_point(const LikParams& lp, double fm, double fv, double 
             const double m = exp(logm);
             const double t = 1.0 + m * alpha;
             const double lt = log(t);
-            const double l = y * (logm + lp.log_alpha - lt) - k * lt;
-            const double dl = (y - m) / t;
+            double l = y * (logm + lp.log_alpha - lt) - k * lt;
+            double dl = (y - m) / t;
             const double dal = y * ia + lt * ia2 - (y + k) * m / t;
+            nb_corner_cases(m, y, l, dl);
             ve = fma(w, l, ve);
             gm = fma(w, dl, gm);
             gz = fma(w * z, dl, gz);

@@ -31,6 +31,7 @@ static_assert(FZ_WPR == 1, "the fused evaluator is written for 8 warps (256 thre
 // thread 0 accumulates SM-clock deltas between phase boundaries of every evaluation into g_phase_prof.
 #ifdef GPC_PHASE_PROF
 __device__ unsigned long long g_phase_prof[16];
+__device__ unsigned long long g_opt_prof[8];      // optimiser phases (lbfgsb.cuh), [7] = iterations
 #define PROF_DECL long long prof_t = clock64(); long long prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
 #define PROF_MARK(k) do { const long long t_ = clock64(); prof_acc[k] += t_ - prof_t; prof_t = t_; } while (0)
 #define PROF_FLUSH do { if (threadIdx.x == 0) { for (int q_ = 0; q_ < 12; ++q_) atomicAdd(&g_phase_prof[q_], (unsigned long long)prof_acc[q_]); atomicAdd(&g_phase_prof[15], 1ull); } } while (0)
@@ -267,9 +268,10 @@ __device__ __forceinline__ LikPart lik_nodes(const LikParams& lp, double fm, dou
             const double t = 1.0 + m * alpha;
             const double lt = log(t);
             const double it = 1.0 / t;                       // one reciprocal instead of two FP64 divisions per node
-            const double l = y * (logm + lp.log_alpha - lt) - k * lt;
-            const double dl = (y - m) * it;
+            double l = y * (logm + lp.log_alpha - lt) - k * lt;
+            double dl = (y - m) * it;
             const double dal = y * ia + lt * ia2 - (y + k) * (m * it);
+            nb_corner_cases(m, y, l, dl);
             o.ve = fma(w, l, o.ve); o.gm = fma(w, dl, o.gm); o.gz = fma(w * z, dl, o.gz); o.da = fma(w, dal, o.da);
         } else {   // ZINB, see lik.cuh for the reference-faithful psi arithmetic
             const double F = fm + sd * z;
@@ -334,9 +336,10 @@ __device__ __forceinline__ LikPart lik_nodes_nb(const LikParams& lp, double fm, 
     for (int q = 0; q < NK; ++q) {
         const double it = gpc_rcp(t[q]);
         const double mit = m[q] * it;
-        const double l = fma(y, (F[q] + lp.log_alpha) - lt[q], -k * lt[q]);
-        const double dl = (y - m[q]) * it;
+        double l = fma(y, (F[q] + lp.log_alpha) - lt[q], -k * lt[q]);
+        double dl = (y - m[q]) * it;
         const double dal = fma(lt[q], ia2, y * k) - (y + k) * mit;
+        nb_corner_cases(m[q], y, l, dl);
         o.ve = fma(w[q], l, o.ve); o.gm = fma(w[q], dl, o.gm); o.gz = fma(w[q] * z[q], dl, o.gz); o.da = fma(w[q], dal, o.da);
     }
     return o;
@@ -360,7 +363,7 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
     if (tid == 0) {
         const Hyper h0 = hyper_from_theta(md, theta);
         kern_setup(fs->kp, md, h0.var, h0.ls);
-        lik_setup(fs->lp, md.lik, h0.alpha, h0.km);
+        lik_setup<true>(fs->lp, md.lik, h0.alpha, h0.km);
         fs->cfg.kernel = md.kernel; fs->cfg.lik = md.lik; fs->cfg.n_off = md.n_off; fs->cfg.row = ws.row;
         fs->cfg.X = md.X; fs->cfg.tmY = ws.tmY; fs->cfg.tmS = ws.tmS;
     }
@@ -380,22 +383,37 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
     if (tid < 64) fs->qmu[tid] = tid < M ? q_mu[tid] : 0.0;
     for (int i = tid; i < FZ_NW * 64; i += GPC_THREADS) (&fs->gqw[0][0])[i] = 0.0;
     __syncthreads();
-#pragma unroll 4
-    for (int idx = tid; idx < 64 * 64; idx += GPC_THREADS) {
-        const int i = idx >> 6, j = idx & 63;
-        double lq = (i == j) ? 1.0 : 0.0, kv = 0.0;       // identity padding: W = 0 outside the leading M x M block
-        if (i < M && j < M) {
-            lq = (j <= i) ? lq_packed[tri_index(i, j)] : 0.0;
-            if (j <= i) {
-                bool cross;
-                const double r2 = kern_r2(kp, fs->Zs + i * dd, fs->Zs + j * dd, cross);
-                kv = kern_val(kp, r2, cross) + (i == j ? shift : 0.0);
+    {
+        // thread owns column j = tid & 63, rows (tid >> 6) + FZ_LPC t: the packed Lq loads are issued together, the Gram
+        // entries go through the vectorised branch-free exp (RBF / Constant only on this path), eight at a time
+        const int j = tid & 63, ib = tid >> 6;
+        const double z0 = fs->Zs[j * dd], z1 = dd > 1 ? fs->Zs[j * dd + 1] : 0.0;
+        const double ce = -0.5 * kp.inv_ls2;
+        const bool rbf0 = md.kernel != GPC_CONST;
+#pragma unroll 1
+        for (int h = 0; h < FZ_RPT / 8; ++h) {
+            double lqv[8], ev[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int i = ib + FZ_LPC * (8 * h + t);
+                lqv[t] = (i < M && j <= i) ? lq_packed[tri_index(i, j)] : ((i == j) ? 1.0 : 0.0);   // identity padding: W = 0 outside M x M
+                const double u = fs->Zs[i * dd] - z0;
+                double r = u * u;
+                if (dd > 1) { const double v = fs->Zs[i * dd + 1] - z1; r = fma(v, v, r); }
+                ev[t] = rbf0 ? ce * r : 0.0;
+            }
+            gpc_exp_v<8>(ev, ev);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int i = ib + FZ_LPC * (8 * h + t);
+                double kv = (i < M && j <= i) ? kp.var * ev[t] + (i == j ? shift : 0.0) : 0.0;
+                if (i >= M && i == j) kv = 1.0;            // identity padding: the blocked factorisation runs on whole 8-blocks
+                fs->T1[i * FZ_LD + j] = lqv[t];
+                fs->T2[i * FZ_LD + j] = kv;
+                fs->Linv[i * FZ_LD + j] = (i == j) ? 1.0 : 0.0;
+                if (need_kg) ws.K0[(8 * h + t) * GPC_THREADS + tid] = ev[t];    // K0_ij / var, re-read for <Kbar, dKuu> in the end phase
             }
         }
-        if (i >= M && i == j) kv = 1.0;                    // identity padding: the blocked factorisation runs on whole 8-blocks
-        fs->T1[i * FZ_LD + j] = lq;
-        fs->T2[i * FZ_LD + j] = kv;
-        fs->Linv[i * FZ_LD + j] = (i == j) ? 1.0 : 0.0;
     }
     if (tid == 0) fs->chol_ok = 1;
     __syncthreads();
@@ -427,7 +445,7 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
                 const double xa[2] = {lp.k + yy, yy + 1.0};
                 double lg[2], dg[2];
                 gpc_lgamma_digamma_v<2>(xa, lg, dg);                         // branch-free, two chains (fastmath.cuh)
-                sum_ve += (lg[0] - lp.lgamma_k) - lg[1];
+                sum_ve += (lg[0] - lg[1]) - lp.lgamma_k;          // the reference's order: at large k it absorbs lgamma(y + 1)
                 sum_da += -k2 * (dg[0] - lp.digamma_k);
             }
             if (md.lik == GPC_NB && scale) sum_ve += yy * gpc_log(scale[n]);  // log m = F + log s (see lik_nodes_nb)
@@ -918,6 +936,11 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
     if (need_kg) {
         double acc[8][2];
         const int r0 = warp * 8;
+        // the thread's sixteen K0_ij / var of the set-up phase come back from the slot (same thread -> entry map: column
+        // j = tid & 63, rows (tid >> 6) + FZ_LPC t); issued here, consumed after the four products below
+        double evs[FZ_RPT];
+#pragma unroll
+        for (int t = 0; t < FZ_RPT; ++t) evs[t] = ws.K0[t * GPC_THREADS + tid];
         // Lm-bar = -tril(Linv^T G) -> T1 (lower, zero upper):  (Linv^T G)[i][j] = sum_{k >= i} Linv[k][i] G[k][j]
         if (active) {
             acc_zero(acc);
@@ -967,41 +990,23 @@ __device__ __forceinline__ int eval_svgp_fused_impl(const ModelDev& md, const do
             acc_store(acc, fs->T3, r0, 0, 8);
         }
         __syncthreads();
-        // <Kbar, dKuu/dvar>, <Kbar, dKuu/dls>: the Gram entries are recomputed (vectorised exp, same thread -> entry map as
-        // the Kuf tiles: column j = tid & 63, rows (tid >> 6) + FZ_LPC t); RBF / Constant only on this path
+        // <Kbar, dKuu/dvar>, <Kbar, dKuu/dls> (RBF / Constant only on this path; K0_ij / var = 1 for the Constant kernel)
         double a2[2] = {0.0, 0.0};
         {
             const int j = tid & 63, ib = tid >> 6;
             const bool jv = j < M;
-            if (md.kernel == GPC_CONST) {
+            const double z0 = fs->Zs[j * dd], z1 = dd > 1 ? fs->Zs[j * dd + 1] : 0.0;
 #pragma unroll
-                for (int t = 0; t < FZ_RPT; ++t) {
-                    const int i = ib + FZ_LPC * t;
-                    if (jv && i < M) a2[0] += fs->T3[i * FZ_LD + j];
-                }
-            } else {
-                const double z0 = fs->Zs[j * dd], z1 = dd > 1 ? fs->Zs[j * dd + 1] : 0.0;
-                const double ce = -0.5 * kp.inv_ls2;
-                double r2[FZ_RPT], ev[FZ_RPT];
-#pragma unroll
-                for (int t = 0; t < FZ_RPT; ++t) {
-                    const int i = ib + FZ_LPC * t;
-                    const double u = fs->Zs[i * dd] - z0;
-                    double r = u * u;
-                    if (dd > 1) { const double v = fs->Zs[i * dd + 1] - z1; r = fma(v, v, r); }
-                    r2[t] = r;
-                    ev[t] = ce * r;
-                }
-                gpc_exp_v<FZ_RPT>(ev, ev);
-#pragma unroll
-                for (int t = 0; t < FZ_RPT; ++t) {
-                    const int i = ib + FZ_LPC * t;
-                    const double gk = (jv && i < M) ? fs->T3[i * FZ_LD + j] * ev[t] : 0.0;     // Kbar_ij * K0_ij / var
-                    a2[0] += gk;
-                    a2[1] = fma(gk, r2[t], a2[1]);
-                }
-                a2[1] *= kp.var * kp.inv_ls3;
+            for (int t = 0; t < FZ_RPT; ++t) {
+                const int i = ib + FZ_LPC * t;
+                const double u = fs->Zs[i * dd] - z0;
+                double r = u * u;
+                if (dd > 1) { const double v = fs->Zs[i * dd + 1] - z1; r = fma(v, v, r); }
+                const double gk = (jv && i < M) ? fs->T3[i * FZ_LD + j] * evs[t] : 0.0;        // Kbar_ij * K0_ij / var
+                a2[0] += gk;
+                a2[1] = fma(gk, r, a2[1]);
             }
+            a2[1] *= kp.var * kp.inv_ls3;
         }
         cta_sum_n<2>(a2, fs->red);
         // RBF / Constant: d Kuf / d var = Kuf / var, so <S, dKuf/dvar> = <Abar, A> / var

@@ -64,9 +64,10 @@ __device__ __forceinline__ SmallPart small_nodes_nb(const LikParams& lp, double 
 #pragma unroll
     for (int q = 0; q < NK; ++q) {
         const double it = gpc_rcp(t[q]);
-        const double l = fma(y, (F[q] + lp.log_alpha) - lt[q], -k * lt[q]);
-        const double dl = (y - m[q]) * it;
+        double l = fma(y, (F[q] + lp.log_alpha) - lt[q], -k * lt[q]);
+        double dl = (y - m[q]) * it;
         const double dal = fma(lt[q], ia2, y * k) - (y + k) * (m[q] * it);
+        nb_corner_cases(m[q], y, l, dl);
         o.ve = fma(w[q], l, o.ve); o.gm = fma(w[q], dl, o.gm); o.gz = fma(w[q] * z[q], dl, o.gz); o.da = fma(w[q], dal, o.da);
     }
     return o;
@@ -133,7 +134,7 @@ __device__ __noinline__ int eval_vgp_small(const ModelDev& md, const double* y, 
     if (tid == 0) {
         hd->h = hyper_from_theta(md, theta);
         kern_setup(hd->kp, md, hd->h.var, hd->h.ls);
-        lik_setup(hd->lp, md.lik, hd->h.alpha, hd->h.km);
+        lik_setup<true>(hd->lp, md.lik, hd->h.alpha, hd->h.km);
         hd->ok = 1;
     }
     const double* q_mu = theta + GPC_NHYP;
@@ -275,7 +276,7 @@ __device__ __noinline__ int eval_vgp_small(const ModelDev& md, const double* y, 
                     const double xa[2] = {lp.k + yy, yy + 1.0};
                     double lg[2], dg[2];
                     gpc_lgamma_digamma_v<2>(xa, lg, dg);
-                    ve += (lg[0] - lp.lgamma_k) - lg[1];
+                    ve += (lg[0] - lg[1]) - lp.lgamma_k;        // the reference's order: at large k it absorbs lgamma(y + 1)
                     da += -(lp.k * lp.k) * (dg[0] - lp.digamma_k);
                     if (md.lik == GPC_NB && scale) ve += yy * gpc_log(sc);      // log m = F + log s
                 }

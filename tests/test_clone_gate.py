@@ -3,7 +3,7 @@
 DESIGN.md section 3: the clone of `eval_svgp_fused` that `k_fit` reaches reacts to unrelated edits of the kernel (a
 batched dot-product pass in the optimiser cost the evaluator 25 % of its speed).  The accepted frame consists of the
 ABI entry/exit saves only.  If this test fails after a change, measure `python bench.py --steps 1 --warmup 1 --no-cpu
-` (`time_split.us_per_eval_in_fit`, 292 us for the accepted frame) and either undo the change or update
+` (`time_split.us_per_eval_in_fit`, ~250 us for the accepted frame) and either undo the change or update
 `tools/clone_gate.py::ACCEPTED` together with the measurement in DESIGN.md."""
 import importlib.util
 import os

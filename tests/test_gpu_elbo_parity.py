@@ -139,3 +139,42 @@ def test_not_positive_definite_is_reported():
     elbo, grad, status = engine.elbo_grad(model, Y, None, theta)
     assert status.tolist() == [0, 1]
     assert torch.isnan(elbo[1]) and torch.isfinite(elbo[0])
+
+
+@pytest.mark.parametrize("kind,N,M", [("SVGP", 150, 20), ("VGP", 30, 0), ("VGP", 80, 0)])
+@pytest.mark.parametrize("case", ["overflow", "underflow", "underflow_positive_counts", "alpha_to_zero"])
+def test_nb_objective_at_wild_trial_points_has_the_references_ieee_class(kind, N, M, case):
+    """Line searches of the reference visit trial points where exp(F) over- or underflows, or alpha -> 0.  There the
+    reference's NB log-density Y log(m / (m + k)) - k log(1 + m alpha) is NaN or -inf by IEEE rules (TensorFlow / the
+    oracle evaluate it literally) and lgamma(k + y) - lgamma(k) is exactly 0 once k + y == k; SciPy's line search
+    reacts differently to NaN, inf and finite objectives, so the device must return the same class (fused on-chip,
+    small-N on-chip and dense evaluators):
+      overflow   q_mu pushes F above 709.8 at some nodes: m = inf -> NaN
+      underflow  F below -745.2: m = 0 -> NaN where a count is 0 (0 * -inf), -inf when every count is positive
+      alpha -> 0 k = 1 / alpha ~ 1e39: finite objective (two different lgamma implementations would differ by ~1e25)."""
+    from gpcounts_b200 import engine
+    from oracle import gp_math as gm
+    rng = np.random.default_rng(5)
+    X, Y = synth_counts(2, N, seed=21)
+    if case == "underflow_positive_counts":
+        Y = Y + 1.0
+    Z = X[np.sort(rng.choice(N, M, replace=False))].copy() if kind == "SVGP" else None
+    spec = gm.ModelSpec(kind=kind, kernel="RBF", lik="NB", X=X, Z=Z)
+    theta = random_theta(spec, rng, 2)
+    mv = spec.Mv
+    if case == "overflow":
+        theta[:, 4:4 + mv] = 900.0
+    elif case.startswith("underflow"):
+        theta[:, 4:4 + mv] = -900.0
+    else:
+        theta[:, 2] = -91.0
+    model = engine.Model(kind, "RBF", "NB", X, Z=Z)
+    elbo, grad, status = engine.elbo_grad(model, Y, None, theta)
+    elbo, status = elbo.cpu().numpy(), status.cpu().numpy()
+    for g in range(2):
+        f_ref, _ = gm.elbo_and_grad(theta[g], spec, Y[g], None)
+        cls = lambda v: "nan" if np.isnan(v) else ("-inf" if v == -np.inf else ("+inf" if v == np.inf else "finite"))
+        assert status[g] == 0
+        assert cls(elbo[g]) == cls(f_ref), (case, g, elbo[g], f_ref)
+        if np.isfinite(f_ref):
+            assert abs(elbo[g] - f_ref) <= 1e-6 * abs(f_ref), (case, g, elbo[g], f_ref)

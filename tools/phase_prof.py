@@ -33,7 +33,7 @@ models = [engine.Model("SVGP", "RBF", "NB", X, Z=Z, restart=rt), engine.Model("S
 h = np.zeros((D, 2, 4)); h[:, :, 0] = host.default_variance(Y, "Negative_binomial", True)[:, None]; h[:, :, 1] = ls0; h[:, :, 2] = 1; h[:, :, 3] = 35
 lib = _lib.load()
 lib.gpc_dbg_phase_prof.argtypes = [C.c_int, C.c_void_p]
-out = (C.c_ulonglong * 16)()
+out = (C.c_ulonglong * 24)()
 names = ["setup(Z,Lq,Kuu,W)", "cholesky", "tri-inverse", "Lm save,u,lgamma pre-pass", "tile load + Kuf exp", "A = Linv Kuf", "C = W A",
          "stats + quadrature", "rank update H += A D A^T", "end phase", "S product Linv^T C", "S epilogue + gq"]
 for variant in (-1, 0):
@@ -46,5 +46,10 @@ for variant in (-1, 0):
     print("evaluations %d, cycles per evaluation %.0f (%.1f us at 1965 MHz)" % (n, tot / n, tot / n / 1965))
     for i, nm in enumerate(names):
         print("  %-32s %8.0f cycles  %5.1f %%" % (nm, out[i] / n, 100.0 * out[i] / tot))
+    nit = max(out[23], 1)
+    onames = ["direction pass", "trial point x = xold + stp d", "gradient pass + line-search step", "BFGS update (s, y stored)", "dot products with the memory", "small matrices (formt / formk / subsm)"]
+    print("  optimiser, cycles per iteration (%d iterations):" % nit)
+    for i, nm in enumerate(onames):
+        print("    %-40s %8.0f" % (nm, out[16 + i] / nit))
     s = st.cpu().numpy()
     print("  fit cycles per evaluation %.0f, eval share %.3f" % (s[..., 13].sum() / s[..., 9].sum(), s[..., 12].sum() / s[..., 13].sum()))
