@@ -227,14 +227,26 @@ def test_c5_headline_sample():
     assert np.all(np.abs(got[well, 0] - ref[well, 0]) <= LL_RTOL * np.abs(ref[well, 0])), (got[well, 0], ref[well, 0])
     assert np.all(np.abs(got[well, 2] - ref[well, 2]) <= LLR_RTOL * np.abs(ref[well, 2]) + LLR_ATOL)
     # (2) all genes: the dynamic fit ends inside the set of outcomes the oracle itself produces for that gene over 32 starts
-    # perturbed by k * 1e-13 (c5_sample_sparse_nb_runs.npz; for 18 of the 48 genes that set is a continuum up to 2 nats
-    # wide - constant genes whose RBF fit creeps along a flat valley), and so does the LLR
+    # perturbed by k * 1e-13 (c5_sample_sparse_nb_runs.npz), and so does the LLR.  For 18 of the 48 genes that set is a
+    # continuum up to 2 nats wide (constant genes whose RBF fit creeps along a flat valley until SciPy's relative-decrease
+    # rule fires; where it fires is decided by round-off).  A fresh draw from a continuous distribution falls outside the range
+    # of 34 samples with probability 2 / 35, i.e. about one of the 17 continuum genes per run (P(>= 4) = 2 %): up to three
+    # continuum genes may lie outside their envelope, by no more than the widest envelope of the fixture (2.2 nats - the scale
+    # of the valley noise; a restart or a premature stop lands 10+ nats away); every other gene lies inside.  The
+    # distributional criteria on 2000 genes are in test_gpu_fit_large.py.
     runs = np.c_[_load("c5_sample_sparse_nb_runs")["ll_runs"], ref[:, 0], ref2[:, 0]]
     tol0 = 1e-4 * np.abs(ref[:, 0])
+    width = runs.max(axis=1) - runs.min(axis=1)
     lo, hi = runs.min(axis=1) - tol0, runs.max(axis=1) + tol0
-    assert np.all((got[:, 0] >= lo) & (got[:, 0] <= hi)), np.c_[got[:, 0], lo, hi][(got[:, 0] < lo) | (got[:, 0] > hi)]
+    continuum = width > 0.05
+    assert 10 <= continuum.sum() <= 24, continuum.sum()
+    outside = (got[:, 0] < lo) | (got[:, 0] > hi)
+    assert not (outside & ~continuum).any(), np.c_[got[:, 0], lo, hi][outside & ~continuum]
+    assert outside.sum() <= 3, np.c_[got[:, 0], lo, hi][outside]
+    assert np.all((got[:, 0] >= lo - width.max()) & (got[:, 0] <= hi + width.max())), np.c_[got[:, 0], lo, hi, width][outside]
     cst_err = np.abs(got[:, 1] - ref[:, 1])
-    assert np.all((got[:, 2] >= lo - ref[:, 1] - cst_err - 1e-9) & (got[:, 2] <= hi - ref[:, 1] + cst_err + 1e-9))
+    ins = ~outside
+    assert np.all((got[ins, 2] >= (lo - ref[:, 1] - cst_err - 1e-9)[ins]) & (got[ins, 2] <= (hi - ref[:, 1] + cst_err + 1e-9)[ins]))
     spread = np.abs(ref[:, 2] - ref2[:, 2])
     err = np.abs(got[:, 2] - ref[:, 2])
     assert np.median(err) <= max(3 * np.median(spread), 2e-3), (np.median(err), np.median(spread))
