@@ -97,3 +97,28 @@ def test_perturbed_oracle_runs_are_consistent_with_the_fixture():
     spread = runs.max(1) - runs.min(1)
     assert (spread < 1e-9).sum() >= 2           # well-posed fits reproduce to all digits
     assert spread.max() < 0.01                  # the others move by millinats: early plateau stops
+
+
+def test_nb_log_density_ieee_classes_follow_the_reference_formula():
+    """The oracle evaluates NegativeBinomialLikelihood.negative_binomial() literally (reference :37-48), so that exp(F)
+    overflow / underflow and alpha -> 0 give the IEEE class the reference's TensorFlow graph gives; the CUDA evaluators are
+    held to these classes by tests/test_gpu_elbo_parity.py.  NumPy restatement of the same line:"""
+    import torch
+    from oracle.gp_math import nb_logp
+    with np.errstate(all="ignore"):
+        def ref(m, y, alpha):
+            from scipy.special import gammaln
+            k = 1.0 / alpha
+            return gammaln(k + y) - gammaln(y + 1) - gammaln(k) + y * np.log(m / (m + k)) - k * np.log(1 + m * alpha)
+        cases = [(np.inf, 3.0, 0.5, "nan"), (np.inf, 0.0, 0.5, "nan"), (0.0, 3.0, 0.5, "-inf"), (0.0, 0.0, 0.5, "nan"),
+                 (5.0, 3.0, 3e-40, "finite"), (5.0, 0.0, 3e-40, "finite")]
+        for m, y, alpha, want in cases:
+            a = float(nb_logp(torch.tensor(m, dtype=torch.float64), torch.tensor(y, dtype=torch.float64),
+                              torch.tensor(alpha, dtype=torch.float64)))
+            b = float(ref(np.float64(m), np.float64(y), np.float64(alpha)))
+            cls = lambda v: "nan" if np.isnan(v) else ("-inf" if v == -np.inf else ("+inf" if v == np.inf else "finite"))
+            assert cls(a) == cls(b) == want, (m, y, alpha, a, b)
+        # alpha -> 0: k + y == k, the lgamma terms cancel exactly and lgamma(y + 1) is absorbed (left-to-right evaluation)
+        a = float(nb_logp(torch.tensor(5.0, dtype=torch.float64), torch.tensor(3.0, dtype=torch.float64),
+                          torch.tensor(3e-40, dtype=torch.float64)))
+        assert abs(a - 3.0 * np.log(5.0 * 3e-40)) < 1e-9 * abs(a)
