@@ -10,8 +10,9 @@
 //     RBF only:  S = u g_m^T + (Lm^-T C) diag(2 g_v) with u = Lm^-T q_mu, consumed in registers for <S o Kuf, R^2>
 // and after the last tile  grad Lq = tril(H Lq) - (Lq - diag(1/Lq_ii)),  Lm-bar = -tril(Lm^-T (q_mu gq^T + W H)).
 // The triangular solves are products with the explicit inverse of the 64 x 64 factor (formed once per evaluation in
-// shared memory); all products run on the FP64 tensor pipe (DMMA m8n8k4), one 8-row block of the output per warp so
-// that the triangular k-ranges are warp-uniform, row blocks paired (w, nrb-1-w) so that every warp does the same work.
+// shared memory); all products run on the FP64 tensor pipe (DMMA m8n8k4).  In the tile loop a warp owns eight data columns
+// of the tile and carries them through the whole chain (see "column tiles" below); the set-up and end phases split their
+// M x M products by 8-row blocks over the warps.
 #pragma once
 #include "model.cuh"
 #include "fastmath.cuh"
@@ -19,13 +20,10 @@
 #define FZ_LD 68                    // leading dimension of every smem matrix (== 4 mod 16: conflict-free DMMA fragments)
 #define FZ_MAT (64 * FZ_LD)         // doubles per 64 x 64 smem matrix
 #define FZ_NW (GPC_THREADS / 32)    // warps per CTA: 8 or 16
-#define FZ_WPR (FZ_NW / 8)          // warps sharing one pair of row blocks: 1 or 2
-#define FZ_TPH (4 / FZ_WPR)         // column tiles per warp in each half of an M x 64 product: 4 or 2
-#define FZ_RT (8 / FZ_WPR)          // rank-update tiles per warp and matrix: 8 or 4
 #define FZ_LPC (GPC_THREADS / 64)   // lanes per data column in the statistics / quadrature phase: 4 or 8
 #define FZ_RPT (64 / FZ_LPC)        // rows per thread when a thread owns a column: 16 or 8
 
-static_assert(FZ_WPR == 1, "the fused evaluator is written for 8 warps (256 threads)");
+static_assert(FZ_NW == 8, "the fused evaluator is written for 8 warps (256 threads): one 8-column slab of a tile per warp");
 
 // Phase timers (tools/phase_prof.py builds a separate profiling library with -DGPC_PHASE_PROF; the product build has none):
 // thread 0 accumulates SM-clock deltas between phase boundaries of every evaluation into g_phase_prof.
@@ -123,56 +121,10 @@ __device__ __forceinline__ void warp_mma(double (&acc)[8][2], const double* __re
     }
 }
 
-// NT column tiles ctb .. ctb+NT-1 of row block r0 (the balanced half-row-block unit of the M x 64 products).
-template <bool AT, bool BT, int NT>
-__device__ __forceinline__ void warp_mmaT(double (&acc)[NT][2], const double* __restrict__ A, int r0,
-                                          const double* __restrict__ B, int kbeg, int kend, int ctb) {
-    const int lane = threadIdx.x & 31, ar = lane >> 2, ak = lane & 3;
-#pragma unroll 2
-    for (int k0 = kbeg; k0 < kend; k0 += 4) {
-        const double a = AT ? A[(k0 + ak) * FZ_LD + r0 + ar] : A[(r0 + ar) * FZ_LD + k0 + ak];
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            const int ct = ctb + t;
-            const double b = BT ? B[(ct * 8 + ar) * FZ_LD + k0 + ak] : B[(k0 + ak) * FZ_LD + ct * 8 + ar];
-            dmma884(acc[t], a, b);
-        }
-    }
-}
-
 template <int NT>
 __device__ __forceinline__ void accT_zero(double (&acc)[NT][2]) {
 #pragma unroll
     for (int t = 0; t < NT; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
-}
-
-template <int NT>
-__device__ __forceinline__ void accT_store(const double (&acc)[NT][2], double* C, int r0, int ctb) {
-    const int lane = threadIdx.x & 31, ar = lane >> 2, ac = 2 * (lane & 3);
-#pragma unroll
-    for (int t = 0; t < NT; ++t)
-        *reinterpret_cast<double2*>(&C[(r0 + ar) * FZ_LD + (ctb + t) * 8 + ac]) = make_double2(acc[t][0], acc[t][1]);
-}
-
-// Rank update over the 64 columns of a tile with the A fragment scaled per column:
-//   acc[t] += (A diag(s)) * B^T for column tiles ct = ct0 + t * FZ_WPR < ct_end  (row block r0 of the M x M result).
-__device__ __forceinline__ void warp_mma_rank(double (&acc)[FZ_RT][2], const double* __restrict__ A, int r0,
-                                              const double* __restrict__ B, const double* __restrict__ s, int ct0,
-                                              int ct_end) {
-    const int lane = threadIdx.x & 31, ar = lane >> 2, ak = lane & 3;
-#pragma unroll 2
-    for (int k0 = 0; k0 < 64; k0 += 4) {
-        double a = A[(r0 + ar) * FZ_LD + k0 + ak];
-        if (s) a *= s[k0 + ak];
-#pragma unroll
-        for (int t = 0; t < FZ_RT; ++t) {
-            const int ct = ct0 + t * FZ_WPR;
-            if (ct < ct_end) {
-                const double b = B[(ct * 8 + ar) * FZ_LD + k0 + ak];
-                dmma884(acc[t], a, b);
-            }
-        }
-    }
 }
 
 __device__ __forceinline__ void acc_zero(double (&acc)[8][2]) {
